@@ -1,0 +1,242 @@
+"""ctypes binding of include/dnaf_b200.h.
+
+There is no CPU fallback: if the CUDA library is missing or no GPU is visible, every entry point
+raises.  The library is built in-tree by ``python -m dna_factory_b200.build`` (or __graft_entry__.build()).
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from .build import LIB_PATH
+
+KMAX = 4
+CLASS_AUTO, CLASS_X, CLASS_Y, CLASS_MT = 0, 1, 2, 3
+E_ARG, E_CUDA, E_NOMEM, E_SPACE, E_SINK, E_INPUT = -1, -2, -3, -4, -5, -6
+
+SINK_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint8), ctypes.c_uint64)
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [("rows", ctypes.c_uint64), ("calls", ctypes.c_uint64), ("text_bytes", ctypes.c_uint64),
+                ("bgzf_bytes", ctypes.c_uint64), ("bgzf_blocks", ctypes.c_uint64), ("crc_xor", ctypes.c_uint32),
+                ("kernel_launches", ctypes.c_uint32), ("ms_sample", ctypes.c_float), ("ms_format", ctypes.c_float),
+                ("ms_deflate", ctypes.c_float), ("ms_fused", ctypes.c_float), ("ms_total", ctypes.c_float)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class DnafError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("dnaf_b200 error %d: %s" % (code, message))
+        self.code = code
+
+
+# every symbol include/dnaf_b200.h declares (tests check the built library exports all of them)
+EXPORTS = ["dnaf_abi_version", "dnaf_last_error", "dnaf_create", "dnaf_destroy", "dnaf_set_stream",
+           "dnaf_set_chunk_bytes", "dnaf_set_row_base", "dnaf_set_fused", "dnaf_set_samples", "dnaf_set_snps", "dnaf_set_overrides",
+           "dnaf_plan", "dnaf_generate", "dnaf_generate_stream", "dnaf_generate_device", "dnaf_genotypes",
+           "dnaf_text", "dnaf_bgzf_compress", "dnaf_bgzf_bound", "dnaf_bgzf_eof"]
+
+_lib = None
+
+
+def load():
+    """Load the CUDA library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("%s is missing: run `python -m dna_factory_b200.build` (needs nvcc). "
+                          "dna_factory_b200 has no CPU fallback." % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    vp, u8p, u32p, u64p = ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint8), ctypes.POINTER(ctypes.c_uint32), \
+        ctypes.POINTER(ctypes.c_uint64)
+    u64, i32 = ctypes.c_uint64, ctypes.c_int
+    sp = ctypes.POINTER(Stats)
+    sig = {
+        "dnaf_abi_version": (i32, []),
+        "dnaf_last_error": (ctypes.c_char_p, [vp]),
+        "dnaf_create": (i32, [i32, ctypes.POINTER(vp)]),
+        "dnaf_destroy": (None, [vp]),
+        "dnaf_set_stream": (i32, [vp, vp]),
+        "dnaf_set_chunk_bytes": (i32, [vp, u64]),
+        "dnaf_set_row_base": (i32, [vp, u64]),
+        "dnaf_set_fused": (i32, [vp, i32]),
+        "dnaf_set_samples": (i32, [vp, ctypes.c_uint32, u8p, u8p]),
+        "dnaf_set_snps": (i32, [vp, u64, u8p, u8p, u32p, u8p, u64p]),
+        "dnaf_set_overrides": (i32, [vp, u64, u64p, u32p]),
+        "dnaf_plan": (i32, [vp, u64, u64, u64p, u64p]),
+        "dnaf_generate": (i32, [vp, u64, u64, u64, i32, i32, u8p, u64, sp]),
+        "dnaf_generate_stream": (i32, [vp, u64, u64, u64, i32, i32, SINK_FN, vp, sp]),
+        "dnaf_generate_device": (i32, [vp, u64, u64, u64, i32, i32, sp]),
+        "dnaf_genotypes": (i32, [vp, u64, u64, u64, u8p, u64]),
+        "dnaf_text": (i32, [vp, u64, u64, u64, u8p, u64, u64p]),
+        "dnaf_bgzf_compress": (i32, [vp, u8p, u64, i32, u8p, u64, sp]),
+        "dnaf_bgzf_bound": (u64, [u64]),
+        "dnaf_bgzf_eof": (i32, [u8p]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+def _u8(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))
+
+
+class Engine:
+    """One GPU context.  Thin, numpy-in / bytes-out wrapper over the C ABI."""
+
+    def __init__(self, device=0):
+        self._lib = load()
+        h = ctypes.c_void_p()
+        rc = self._lib.dnaf_create(device, ctypes.byref(h))
+        if rc:
+            raise DnafError(rc, self._lib.dnaf_last_error(None).decode())
+        self._h = h
+        self.n_samples = 0
+        self.n_snps = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.dnaf_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc:
+            raise DnafError(rc, self._lib.dnaf_last_error(self._h).decode())
+
+    # -- configuration
+    def set_stream(self, cuda_stream):
+        self._check(self._lib.dnaf_set_stream(self._h, ctypes.c_void_p(cuda_stream)))
+
+    def set_chunk_bytes(self, n):
+        self._check(self._lib.dnaf_set_chunk_bytes(self._h, n))
+
+    def set_row_base(self, row_base):
+        self._check(self._lib.dnaf_set_row_base(self._h, row_base))
+
+    def set_fused(self, enable):
+        self._check(self._lib.dnaf_set_fused(self._h, 1 if enable else 0))
+
+    def set_samples(self, sex, is_control):
+        sex = np.ascontiguousarray(sex, dtype=np.uint8)
+        ctl = np.ascontiguousarray(is_control, dtype=np.uint8)
+        if sex.shape != ctl.shape or sex.ndim != 1:
+            raise ValueError("sex and is_control must be 1-D arrays of equal length")
+        self._check(self._lib.dnaf_set_samples(self._h, len(sex), _u8(sex), _u8(ctl)))
+        self.n_samples = len(sex)
+
+    def set_snps(self, chrom_class, n_alleles, thresholds, prefix_bytes, prefix_off):
+        cls = np.ascontiguousarray(chrom_class, dtype=np.uint8)
+        k = np.ascontiguousarray(n_alleles, dtype=np.uint8)
+        thr = np.ascontiguousarray(thresholds, dtype=np.uint32).reshape(-1)
+        pre = np.ascontiguousarray(prefix_bytes, dtype=np.uint8)
+        off = np.ascontiguousarray(prefix_off, dtype=np.uint64)
+        S = len(cls)
+        if len(k) != S or len(thr) != S * KMAX or len(off) != S + 1:
+            raise ValueError("inconsistent SNP array lengths")
+        if len(pre) < int(off[-1]):
+            raise ValueError("prefix_bytes shorter than prefix_off[-1]")
+        self._check(self._lib.dnaf_set_snps(self._h, S, _u8(cls), _u8(k), thr.ctypes.data_as(
+            ctypes.POINTER(ctypes.c_uint32)), _u8(pre), off.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))))
+        self.n_snps = S
+
+    def set_overrides(self, rows, samples):
+        rows = np.ascontiguousarray(rows, dtype=np.uint64)
+        samples = np.ascontiguousarray(samples, dtype=np.uint32)
+        if len(rows) != len(samples):
+            raise ValueError("rows and samples differ in length")
+        self._check(self._lib.dnaf_set_overrides(self._h, len(rows), rows.ctypes.data_as(
+            ctypes.POINTER(ctypes.c_uint64)), samples.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32))))
+
+    # -- sizes
+    def plan(self, row_begin, row_end):
+        t, b = ctypes.c_uint64(), ctypes.c_uint64()
+        self._check(self._lib.dnaf_plan(self._h, row_begin, row_end, ctypes.byref(t), ctypes.byref(b)))
+        return t.value, b.value
+
+    # -- the hot path
+    def generate(self, row_begin, row_end, seed, level=6, rng_mode=0):
+        """BGZF bytes (whole blocks, no EOF) of rows [row_begin,row_end) -> (bytes, stats dict)."""
+        _, bound = self.plan(row_begin, row_end)
+        out = np.empty(bound, dtype=np.uint8)
+        st = Stats()
+        self._check(self._lib.dnaf_generate(self._h, row_begin, row_end, seed, rng_mode, level, _u8(out), bound,
+                                            ctypes.byref(st)))
+        return out[:st.bgzf_bytes].tobytes(), st.as_dict()
+
+    def generate_into(self, row_begin, row_end, seed, out, level=6, rng_mode=0):
+        """Same, into a caller-owned uint8 numpy buffer; returns stats dict."""
+        st = Stats()
+        self._check(self._lib.dnaf_generate(self._h, row_begin, row_end, seed, rng_mode, level, _u8(out), out.nbytes,
+                                            ctypes.byref(st)))
+        return st.as_dict()
+
+    def generate_stream(self, row_begin, row_end, seed, write, level=6, rng_mode=0):
+        """Calls write(bytes) for consecutive pieces of the stream; returns stats dict."""
+        err = []
+
+        def cb(user, data, n):
+            try:
+                write(ctypes.string_at(data, n))
+                return 0
+            except BaseException as e:  # noqa: surfaced after the call returns
+                err.append(e)
+                return 1
+
+        st = Stats()
+        rc = self._lib.dnaf_generate_stream(self._h, row_begin, row_end, seed, rng_mode, level, SINK_FN(cb), None,
+                                            ctypes.byref(st))
+        if err:
+            raise err[0]
+        self._check(rc)
+        return st.as_dict()
+
+    def generate_device(self, row_begin, row_end, seed, level=6, rng_mode=0):
+        st = Stats()
+        self._check(self._lib.dnaf_generate_device(self._h, row_begin, row_end, seed, rng_mode, level,
+                                                   ctypes.byref(st)))
+        return st.as_dict()
+
+    # -- parity gates
+    def genotypes(self, row_begin, row_end, seed):
+        rows = row_end - row_begin
+        out = np.empty(max(rows * self.n_samples * 2, 1), dtype=np.uint8)
+        self._check(self._lib.dnaf_genotypes(self._h, row_begin, row_end, seed, _u8(out), out.nbytes))
+        return out[:rows * self.n_samples * 2].reshape(rows, self.n_samples, 2)
+
+    def text(self, row_begin, row_end, seed):
+        t, _ = self.plan(row_begin, row_end)
+        out = np.empty(max(t, 1), dtype=np.uint8)
+        n = ctypes.c_uint64()
+        self._check(self._lib.dnaf_text(self._h, row_begin, row_end, seed, _u8(out), out.nbytes, ctypes.byref(n)))
+        return out[:n.value].tobytes()
+
+    def bgzf_compress(self, data, level=6):
+        buf = np.frombuffer(bytes(data) + b"\0", dtype=np.uint8)
+        n = len(buf) - 1
+        bound = int(self._lib.dnaf_bgzf_bound(n))
+        out = np.empty(bound, dtype=np.uint8)
+        st = Stats()
+        self._check(self._lib.dnaf_bgzf_compress(self._h, _u8(buf), n, level, _u8(out), bound, ctypes.byref(st)))
+        return out[:st.bgzf_bytes].tobytes(), st.as_dict()
+
+
+def bgzf_eof():
+    out = np.empty(28, dtype=np.uint8)
+    load().dnaf_bgzf_eof(_u8(out))
+    return out.tobytes()

@@ -1,0 +1,147 @@
+/*
+ * dnaf_b200.h -- C ABI of the B200-native dna-factory population-generation hot path.
+ *
+ * The reference (ochrzan/dna-factory) has no FFI: its seam for this path is the Python method
+ *     PopulationFactory.write_vcf_snps(self, fam_data, snps, file)          pop_factory.py:417-469
+ * which forks workers running
+ *     PopulationFactory.queue_vcf_snps(self, fam_data, work_q, result_p)    pop_factory.py:471-513
+ * and feeds their rows, in SNP order, to Bio.bgzf.BgzfWriter.write()       pop_factory.py:449
+ * (opened at pop_factory.py:403, closed by the `with` at :403-413).
+ * This header is what a ctypes binding of that seam needs: plain pointers and sizes, no Python
+ * objects, no torch types.  INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative DNAF_E_* code; dnaf_last_error() gives text
+ *   - one context per GPU, used from one host thread at a time
+ *   - the caller owns every input buffer for the duration of the call only; the library copies
+ *   - output buffers are host memory owned by the caller unless the name says "device"
+ *   - rows are addressed by their GLOBAL index in the sorted SNP list (pop_factory.py:245); that
+ *     index is also the row word of the Philox counter, so any row range can be regenerated alone
+ */
+#ifndef DNAF_B200_H
+#define DNAF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DNAF_ABI_VERSION 1
+#define DNAF_KMAX 4 /* alleles per SNP the device path handles (A,C,G,T); K=2 for SnpFactory output */
+
+/* chromosome classes -- the only thing is_haploid() (common/snp.py:102-109) looks at */
+#define DNAF_CLASS_AUTO 0 /* diploid for everybody:          "a/b\t"  4 bytes per sample            */
+#define DNAF_CLASS_X 1    /* haploid for males:              2 bytes male, 4 bytes female           */
+#define DNAF_CLASS_Y 2    /* haploid; females print ".":     2 bytes per sample  (pop_factory.py:481) */
+#define DNAF_CLASS_MT 3   /* haploid for everybody:          2 bytes per sample                     */
+
+#define DNAF_OK 0
+#define DNAF_E_ARG (-1)    /* bad argument / call order                    */
+#define DNAF_E_CUDA (-2)   /* CUDA runtime error (message has the detail)  */
+#define DNAF_E_NOMEM (-3)  /* host or device allocation failed             */
+#define DNAF_E_SPACE (-4)  /* caller's output buffer too small             */
+#define DNAF_E_SINK (-5)   /* the sink callback returned non-zero          */
+#define DNAF_E_INPUT (-6)  /* input the reference would raise on (e.g. CDF that does not reach 1.0) */
+
+typedef struct dnaf_ctx dnaf_ctx;
+
+/* Ordered output callback: receives consecutive pieces of the BGZF stream (whole blocks). */
+typedef int (*dnaf_sink_fn)(void* user, const uint8_t* data, uint64_t n_bytes);
+
+typedef struct dnaf_stats {
+    uint64_t rows;             /* SNP rows generated                                       */
+    uint64_t calls;            /* genotype calls = rows * samples                          */
+    uint64_t text_bytes;       /* uncompressed VCF text bytes of those rows                */
+    uint64_t bgzf_bytes;       /* compressed bytes emitted (no EOF block)                  */
+    uint64_t bgzf_blocks;      /* BGZF blocks emitted                                      */
+    uint32_t crc_xor;          /* xor of all block CRC32s ("checksum of checksums")        */
+    uint32_t kernel_launches;  /* kernels of this library launched by the call             */
+    float ms_sample;           /* CUDA-event time of the sampling kernels                  */
+    float ms_format;           /* ... of the text formatter                                */
+    float ms_deflate;          /* ... of the BGZF encoder (+ compaction)                   */
+    float ms_fused;            /* ... of the fused sample+format+deflate kernel            */
+    float ms_total;            /* first launch to last kernel end, on the library stream   */
+} dnaf_stats;
+
+int dnaf_abi_version(void);
+const char* dnaf_last_error(const dnaf_ctx* ctx); /* ctx may be NULL: error of the last failed create */
+
+/* Replaces the worker pool set-up of write_vcf_snps (pop_factory.py:419-434). */
+int dnaf_create(int device_ordinal, dnaf_ctx** out);
+void dnaf_destroy(dnaf_ctx* ctx);
+/* Launch on a caller-provided cudaStream_t (e.g. torch's current stream) instead of the private one. */
+int dnaf_set_stream(dnaf_ctx* ctx, void* cuda_stream);
+/* Upper bound on the uncompressed text handled per internal pass (default 256 MiB; tests shrink it). */
+int dnaf_set_chunk_bytes(dnaf_ctx* ctx, uint64_t text_bytes);
+/* Philox row counter of local row r is row_base + r (default 0): lets a process that holds only a slice
+ * of the sorted SNP list, e.g. one rank of a multi-GPU run, draw the rows it was given. */
+int dnaf_set_row_base(dnaf_ctx* ctx, uint64_t row_base);
+/* 0 = three-kernel path only (sample -> format -> deflate), 1 = fused kernel where it applies (default). */
+int dnaf_set_fused(dnaf_ctx* ctx, int enable);
+
+/*
+ * fam_data (pop_factory.py:341-383): sex[i] is SampleInfo.sex (1 = male, anything else female,
+ * pop_factory.py:70-71); is_control[i] is SampleInfo.is_control.  n_samples may be 0 (sites-only run).
+ */
+int dnaf_set_samples(dnaf_ctx* ctx, uint32_t n_samples, const uint8_t* sex, const uint8_t* is_control);
+
+/*
+ * The sorted SNP list (SNPTuples, pop_factory.py:74-133), flattened:
+ *   chrom_class[r]   DNAF_CLASS_* of snp.chromosome
+ *   n_alleles[r]     len(snp.tuples), 1..DNAF_KMAX
+ *   thresholds[r*4+k] floor(cum_k * 2^32) saturated to 0xFFFFFFFF when cum_k >= 1.0, so that
+ *                    `tuples[k][1] >= u` (pop_factory.py:94) becomes the integer test U <= threshold
+ *                    for u = U * 2^-32; entries k >= n_alleles are ignored
+ *   prefix_bytes / prefix_off[r..r+1]  the 9-column row lead exactly as pop_factory.py:503-507 formats it
+ * Returns DNAF_E_INPUT when the last threshold of a row is not saturated (the reference's
+ * pick_allele_index would return None and "%i" would raise).
+ */
+int dnaf_set_snps(dnaf_ctx* ctx, uint64_t n_snps, const uint8_t* chrom_class, const uint8_t* n_alleles,
+                  const uint32_t* thresholds, const uint8_t* prefix_bytes, const uint64_t* prefix_off);
+
+/*
+ * Cells where the reference takes its forced-minor branch (pop_factory.py:485,495-499): sample is a
+ * case AND `snp.id in sample.deleterious_snps`.  Pairs (global row, sample index), sorted by row.
+ * The host computes them with the reference's own dict-membership semantics.
+ */
+int dnaf_set_overrides(dnaf_ctx* ctx, uint64_t n_pairs, const uint64_t* snp_row, const uint32_t* sample_idx);
+
+/* Sizes of rows [row_begin,row_end): exact text bytes and an upper bound on the BGZF bytes. */
+int dnaf_plan(dnaf_ctx* ctx, uint64_t row_begin, uint64_t row_end, uint64_t* text_bytes, uint64_t* bgzf_bound);
+
+/*
+ * The hot path: rows [row_begin,row_end) -> genotype draws -> VCF text -> BGZF blocks.
+ * Emits whole BGZF blocks that decompress to exactly the text of those rows (first block starts
+ * and last block ends on a row boundary; no header, no EOF block -- the caller writes those).
+ * rng_mode: 0 = replay, 1 = native; both use the same counter-based Philox stream.
+ * level: the -z value, 1..9.
+ */
+int dnaf_generate(dnaf_ctx* ctx, uint64_t row_begin, uint64_t row_end, uint64_t seed, int rng_mode, int level,
+                  uint8_t* out, uint64_t out_cap, dnaf_stats* stats);
+int dnaf_generate_stream(dnaf_ctx* ctx, uint64_t row_begin, uint64_t row_end, uint64_t seed, int rng_mode,
+                         int level, dnaf_sink_fn sink, void* user, dnaf_stats* stats);
+/* Same work, output left in (and then discarded from) device memory: kernel-only timing. */
+int dnaf_generate_device(dnaf_ctx* ctx, uint64_t row_begin, uint64_t row_end, uint64_t seed, int rng_mode,
+                         int level, dnaf_stats* stats);
+
+/* Parity gates. genotypes: out[(r*n_samples+i)*2+s] = allele index, 0xFF where the cell has no such
+ * allele (second slot of a haploid cell, both slots of '.').  text: the uncompressed rows. */
+int dnaf_genotypes(dnaf_ctx* ctx, uint64_t row_begin, uint64_t row_end, uint64_t seed, uint8_t* out,
+                   uint64_t out_cap);
+int dnaf_text(dnaf_ctx* ctx, uint64_t row_begin, uint64_t row_end, uint64_t seed, uint8_t* out, uint64_t out_cap,
+              uint64_t* n_bytes);
+
+/* BgzfWriter.write() for arbitrary bytes (used for the VCF header, pop_factory.py:404-405):
+ * cuts `text` every 65280 bytes and encodes each piece on the GPU.  No EOF block. */
+int dnaf_bgzf_compress(dnaf_ctx* ctx, const uint8_t* text, uint64_t n_bytes, int level, uint8_t* out,
+                       uint64_t out_cap, dnaf_stats* stats);
+uint64_t dnaf_bgzf_bound(uint64_t text_bytes);
+/* The 28-byte BGZF end-of-file block BgzfWriter.close() appends. */
+int dnaf_bgzf_eof(uint8_t* out28);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DNAF_B200_H */

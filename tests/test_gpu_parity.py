@@ -1,0 +1,159 @@
+"""GPU parity tests (run on the B200 box with -m gpu): the CUDA path, called through the C ABI,
+against the committed reference goldens and against the CPU oracle on seeded synthetic inputs."""
+import zlib
+
+import numpy as np
+import pytest
+
+from tests.cases import ROW_CASES, load_case, synth_case
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def native():
+    from dna_factory_b200 import _native, host
+    return _native, host
+
+
+def _engine(native, case, chunk=None, fused=True):
+    _native, host = native
+    eng = _native.Engine(0)
+    host.configure(eng, case.samples, case.snps)
+    if chunk:
+        eng.set_chunk_bytes(chunk)
+    eng.set_fused(fused)
+    return eng
+
+
+def _expected_genotypes(case, text):
+    """Parse the oracle/golden text back into the [rows][N][2] allele matrix (0xFF = absent)."""
+    n = len(case.samples)
+    rows = text.split(b"\n")[:-1]
+    out = np.full((len(rows), n, 2), 0xFF, dtype=np.uint8)
+    for r, line in enumerate(rows):
+        cells = line.split(b"\t")[9:]
+        if n == 0:
+            continue
+        assert len(cells) == n
+        for i, c in enumerate(cells):
+            if c == b".":
+                continue
+            parts = c.split(b"/")
+            out[r, i, 0] = int(parts[0])
+            if len(parts) == 2:
+                out[r, i, 1] = int(parts[1])
+    return out
+
+
+@pytest.mark.parametrize("name", ROW_CASES)
+def test_genotypes_bit_exact_vs_reference_golden(native, name):
+    case = load_case(name)
+    if len(case.samples) == 0:
+        pytest.skip("no genotypes in a sites-only run")
+    eng = _engine(native, case)
+    eng.set_row_base(case.row_begin)
+    got = eng.genotypes(0, len(case.snps), case.seed)
+    assert np.array_equal(got, _expected_genotypes(case, case.text))
+
+
+@pytest.mark.parametrize("name", ROW_CASES)
+def test_text_byte_identical_vs_reference_golden(native, name):
+    case = load_case(name)
+    eng = _engine(native, case)
+    eng.set_row_base(case.row_begin)
+    assert eng.text(0, len(case.snps), case.seed) == case.text
+
+
+@pytest.mark.parametrize("name", ROW_CASES)
+@pytest.mark.parametrize("level", [1, 6, 9])
+def test_bgzf_decompresses_to_reference_golden(native, name, level):
+    import gzip
+    from oracle import oracle
+    case = load_case(name)
+    eng = _engine(native, case)
+    eng.set_row_base(case.row_begin)
+    blob, st = eng.generate(0, len(case.snps), case.seed, level=level)
+    text, blocks, eof = oracle.bgzf_decompress(blob)
+    assert text == case.text
+    assert blocks == st["bgzf_blocks"] and not eof
+    assert st["text_bytes"] == len(case.text)
+    assert gzip.decompress(blob + native[0].bgzf_eof()) == case.text
+
+
+@pytest.mark.parametrize("n,s,seed", [(1, 5, 1), (15, 9, 2), (16, 9, 3), (17, 40, 4), (200, 300, 5), (1000, 64, 6),
+                                      (4097, 24, 7), (20000, 6, 8)])
+def test_oracle_vs_cuda_synthetic(native, n, s, seed):
+    from oracle import oracle
+    case = synth_case(n, s, seed=seed)
+    want, row_off = oracle.rows(case.samples, case.snps, case.seed, 0, n_threads=4)
+    eng = _engine(native, case, chunk=1 << 20)
+    assert np.array_equal(eng.genotypes(0, s, case.seed), _expected_genotypes(case, want))
+    assert eng.text(0, s, case.seed) == want
+    for level in (1, 6):
+        blob, st = eng.generate(0, s, case.seed, level=level)
+        text, blocks, _ = oracle.bgzf_decompress(blob)
+        assert text == want
+        assert st["calls"] == n * s and st["bgzf_blocks"] == blocks
+    # any row range is independently regenerable (counter-based RNG): ranges concatenate
+    mid = s // 2
+    a, _ = eng.generate(0, mid, case.seed, level=2)
+    b, _ = eng.generate(mid, s, case.seed, level=2)
+    assert oracle.bgzf_decompress(a + b)[0] == want
+    sub = eng.text(mid, s, case.seed)
+    assert sub == want[int(row_off[mid]):]
+
+
+def test_bgzf_compress_arbitrary_bytes(native):
+    from oracle import oracle
+    _native, _ = native
+    eng = _native.Engine(0)
+    rs = np.random.RandomState(0)
+    header = ("##fileformat=VCFv4.3\n#CHROM\tPOS\t" + "\t".join(str(100001 + i) for i in range(30000)) + "\n").encode()
+    cases = [b"", b"a", b"abcd" * 5, header, rs.randint(0, 256, 200000).astype(np.uint8).tobytes(),
+             b"0/0\t" * 70000, bytes(range(256)) * 300]
+    for data in cases:
+        blob, st = eng.bgzf_compress(data, level=6)
+        text, blocks, _ = oracle.bgzf_decompress(blob)
+        assert text == data
+        assert blocks == (len(data) + 65279) // 65280
+
+
+def test_stream_sink_and_chunking(native):
+    from oracle import oracle
+    case = synth_case(3000, 50, seed=11)
+    want, _ = oracle.rows(case.samples, case.snps, case.seed, 0, n_threads=4)
+    eng = _engine(native, case, chunk=64 << 10)
+    pieces = []
+    st = eng.generate_stream(0, 50, case.seed, pieces.append, level=3)
+    assert len(pieces) > 1
+    assert oracle.bgzf_decompress(b"".join(pieces))[0] == want
+    dev = eng.generate_device(0, 50, case.seed, level=3)
+    assert dev["bgzf_bytes"] == st["bgzf_bytes"] and dev["crc_xor"] == st["crc_xor"]
+    assert dev["kernel_launches"] > 0
+    # checksum of checksums: xor of the per-block CRC32s in the stream
+    x = 0
+    blob = b"".join(pieces)
+    pos = 0
+    while pos < len(blob):
+        bsize = int.from_bytes(blob[pos + 16:pos + 18], "little") + 1
+        x ^= int.from_bytes(blob[pos + bsize - 8:pos + bsize - 4], "little")
+        pos += bsize
+    assert x == st["crc_xor"]
+
+
+def test_errors_are_loud(native):
+    _native, host = native
+    eng = _native.Engine(0)
+    with pytest.raises(_native.DnafError):
+        eng.generate(0, 1, 1)                      # nothing configured
+    case = synth_case(4, 3, seed=1)
+    host.configure(eng, case.samples, case.snps)
+    with pytest.raises(_native.DnafError):
+        eng.generate(0, 99, 1)                     # row range out of bounds
+    flat = host.flatten_snps(case.snps)
+    flat["thresholds"] = flat["thresholds"].copy()
+    flat["thresholds"][0, 1] = 5                   # CDF does not reach 1.0 -> the reference would raise
+    with pytest.raises(_native.DnafError) as e:
+        eng.set_snps(**flat)
+    assert e.value.code == _native.E_INPUT
