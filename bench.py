@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""Benchmark of the population-generation hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload: BASELINE.json configs[1] (README 8-core scenario): 10 000 cases + 10 000 controls, -f 0.01,
+-z 2, SNPs drawn like SnpFactory (MAF from the RefSNP CDF, chromosomes by CHROMOSOME_PROB, sorted by
+(chromosome string, position)).  One "step" = one batch of ROWS_PER_STEP consecutive SNP rows of that
+5 000 000-row population through the hot path: allele draws -> VCF text -> BGZF blocks.  Every step uses
+a new row window (and every rank its own contiguous SNP range), so inputs never repeat.
+
+  value   calls/s with the SNP table already resident in HBM and the BGZF stream left in HBM
+          (dnaf_generate_device), timed with CUDA events on the stream the kernels run on
+  e2e     calls/s through the public API with HOST buffers: every step uploads that step's SNP metadata
+          (H2D) and receives the BGZF bytes in host memory (D2H) inside the timed region
+  roofline / cpu_baseline: see DESIGN.md section 6
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_CASES = 10000
+N_CONTROLS = 10000
+TOTAL_SNPS = 5_000_000
+MIN_MAF = 0.01
+LEVEL = 2
+MALE_ODDS = 0.5
+ROWS_PER_STEP = 8192
+PHILOX_SEED = 0x5EED000000000001
+HOST_SEED = 20260101
+WORKLOAD = ("C2 pop_factory -s 10000 -c 10000 -x 5000000 -f 0.01 -z 2: one step = %d consecutive SNP rows "
+            "x 20000 samples (sample -> VCF GT text -> BGZF)" % ROWS_PER_STEP)
+
+
+def synth_population(n_rows, rank=0):
+    """Sex vector, control flags and `n_rows` sorted SNP rows shaped like the reference's own generator."""
+    from dna_factory_b200 import snp
+    rs_state = np.random.get_state()
+    np.random.seed(HOST_SEED + rank)
+    n = N_CASES + N_CONTROLS
+    sex = np.where(np.random.rand(n) <= MALE_ODDS, 1, 2).astype(np.uint8)       # pop_factory.py:352,365
+    ctl = (np.arange(n) < N_CONTROLS).astype(np.uint8)                          # pop_factory.py:358
+    table = snp.SnpFactory.init_from_cdf_file().random_snp_table(n_rows, min_maf=MIN_MAF, vector_alt=True).sorted()
+    # polygenic overrides: ~6 deleterious SNPs per case, as deleterious.yml's groups produce
+    n_over = 6 * N_CASES * n_rows // TOTAL_SNPS + 8
+    orow = np.sort(np.random.randint(0, n_rows, n_over)).astype(np.uint64)
+    osamp = np.random.randint(N_CONTROLS, n, n_over).astype(np.uint32)
+    np.random.set_state(rs_state)
+    return sex, ctl, table, orow, osamp
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                     "hw_power_brake_slowdown": 0x80}
+            while not self._stop_evt.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+                time.sleep(0.05)
+        except Exception as e:  # noqa: clocks are reported as unknown, never fatal
+            self.reasons.add("unavailable:%s" % type(e).__name__)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def cpu_reference_run(steps, warmup, budget_s=20.0):
+    """The reference's path on host cores: C port of the row loop + zlib BGZF (oracle/), all host threads.
+    Each step is a bounded sample of the workload (same sample count and level, fewer SNP rows)."""
+    from oracle import oracle
+    oracle.build()
+    cores = oracle.lib().dnaf_or_num_threads()
+    rows = 64
+    sex, ctl, table, orow, osamp = synth_population(rows * (steps + warmup))
+    snps_all = table.to_snps()
+    from types import SimpleNamespace
+    fam = [SimpleNamespace(sex=int(s), is_control=bool(c), deleterious_snps=None if c else {}, person_id=i) for i, (s, c) in
+           enumerate(zip(sex, ctl))]
+    flat_batches = []
+    for k in range(steps + warmup):
+        flat = oracle.flatten(fam, snps_all[k * rows:(k + 1) * rows])
+        sel = (orow >= k * rows) & (orow < (k + 1) * rows)
+        flat["over_row"] = (orow[sel] - k * rows).astype(np.uint64)
+        flat["over_sample"] = osamp[sel]
+        flat_batches.append(flat)
+    times = []
+    text_bytes = 0
+    comp_bytes = 0
+    for k, flat in enumerate(flat_batches):
+        t0 = time.perf_counter()
+        text, _ = oracle.rows_from_flat(flat, PHILOX_SEED, k * rows, n_threads=cores)
+        blob = oracle.bgzf(text.tobytes(), level=LEVEL, with_eof=False, n_threads=cores)
+        dt = time.perf_counter() - t0
+        if k >= warmup:
+            times.append(dt)
+            text_bytes += len(text)
+            comp_bytes += len(blob)
+    calls = rows * (N_CASES + N_CONTROLS) * len(times)
+    total = sum(times)
+    return {"value": calls / total, "ms_per_step": 1e3 * total / len(times), "cores": cores,
+            "sample": "%d steps x %d SNP rows x %d samples, -z %d (C port of pop_factory.py:471-513 + zlib BGZF, "
+                      "OpenMP over rows and blocks)" % (len(times), rows, N_CASES + N_CONTROLS, LEVEL),
+            "text_bytes": text_bytes, "bgzf_bytes": comp_bytes}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows-per-step", type=int, default=ROWS_PER_STEP)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        r = cpu_reference_run(args.steps, args.warmup)
+        line = {"impl": "reference", "metric": "genotype calls/sec to bgzf VCF", "value": r["value"],
+                "unit": "calls/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u32", "data": "synthetic", "config": {"workload": WORKLOAD},
+                "cpu_baseline": {"value": r["value"], "unit": "calls/s", "cores": r["cores"], "kind": "port",
+                                 "sample": r["sample"]},
+                "e2e": {"value": r["value"], "unit": "calls/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from dna_factory_b200 import _native
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: dna_factory_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    R = args.rows_per_step
+    n_steps_total = warmup + args.steps
+    # this rank's contiguous SNP range of the population: rows for the device-resident pass, then for e2e
+    rows_needed = 2 * n_steps_total * R
+    sex, ctl, table, orow, osamp = synth_population(rows_needed, rank)
+    arrays = table.device_arrays()
+    n = len(sex)
+    row_base = rank * (TOTAL_SNPS // max(world, 1))
+
+    eng = _native.Engine(local_rank)
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+    eng.set_samples(sex, ctl)
+    eng.set_snps(**arrays)
+    eng.set_overrides(orow, osamp)
+    eng.set_row_base(row_base)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ------------------------------------------------------------------ device-resident pass (`value`)
+    for k in range(warmup):
+        eng.generate_device(k * R, (k + 1) * R, PHILOX_SEED, level=LEVEL)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stats = []
+    ev0.record(stream)
+    for k in range(warmup, n_steps_total):
+        stats.append(eng.generate_device(k * R, (k + 1) * R, PHILOX_SEED, level=LEVEL))
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
+    calls = sum_over_ranks(sum(s["calls"] for s in stats))
+    text_bytes = sum(s["text_bytes"] for s in stats)
+    bgzf_bytes = sum(s["bgzf_bytes"] for s in stats)
+    launches = int(sum(s["kernel_launches"] for s in stats))
+    value = calls / (ms * 1e-3)
+
+    # dominant kernel: algorithmic bytes = uncompressed text bytes it emits, live CUDA-event time
+    stage_ms = {k: sum(s[k] for s in stats) for k in ("ms_sample", "ms_format", "ms_deflate", "ms_fused")}
+    dom = max(stage_ms, key=stage_ms.get)
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = text_bytes / (stage_ms[dom] * 1e-3) / 1e9 if stage_ms[dom] > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": dom.replace("ms_", ""), "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                "algorithmic_bytes": "uncompressed VCF text bytes emitted (%.3f B/call)" % (text_bytes / max(1, sum(
+                    s["calls"] for s in stats))),
+                "stage_ms_per_step": {k.replace("ms_", ""): v / len(stats) for k, v in stage_ms.items()},
+                "pipeline_frac": (text_bytes / (sum(s["ms_total"] for s in stats) * 1e-3) / 1e9) / peak}
+
+    # ------------------------------------------------------------------ end-to-end pass (`e2e`)
+    # host buffers in, host buffer out: per step the step's SNP metadata goes H2D, the BGZF bytes come D2H
+    out = np.empty(int(eng.plan(0, R)[1]) + (1 << 20), dtype=np.uint8)
+    base = n_steps_total * R
+
+    def step_arrays(k):
+        lo, hi = base + k * R, base + (k + 1) * R
+        p0, p1 = int(arrays["prefix_off"][lo]), int(arrays["prefix_off"][hi])
+        sel = (orow >= lo) & (orow < hi)
+        return (dict(chrom_class=arrays["chrom_class"][lo:hi], n_alleles=arrays["n_alleles"][lo:hi],
+                     thresholds=arrays["thresholds"][lo:hi], prefix_bytes=arrays["prefix_bytes"][p0:p1 + 1],
+                     prefix_off=arrays["prefix_off"][lo:hi + 1] - np.uint64(p0)),
+                (orow[sel] - np.uint64(lo)).astype(np.uint64), osamp[sel], lo)
+
+    batches = [step_arrays(k) for k in range(n_steps_total)]
+
+    def e2e_step(b):
+        a, o_r, o_s, lo = b
+        eng.set_snps(**a)
+        eng.set_overrides(o_r, o_s)
+        eng.set_row_base(row_base + lo)
+        return eng.generate_into(0, R, PHILOX_SEED, out, level=LEVEL)
+
+    for k in range(warmup):
+        e2e_step(batches[k])
+    barrier()
+    t0 = time.perf_counter()
+    e2e_stats = [e2e_step(batches[k]) for k in range(warmup, n_steps_total)]
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e_calls = sum_over_ranks(sum(s["calls"] for s in e2e_stats))
+    h2d = int(np.mean([sum(v.nbytes for v in b[0].values()) + b[1].nbytes + b[2].nbytes for b in
+                       batches[warmup:]]))
+    d2h = int(np.mean([s["bgzf_bytes"] for s in e2e_stats]))
+    launches += 0  # e2e launches are outside the `value` region
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            r = cpu_reference_run(6, 1)
+            cpu = {"value": r["value"], "unit": "calls/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+        line = {"metric": "genotype calls/sec to bgzf VCF", "value": value, "unit": "calls/s", "n_gpus": world,
+                "steps": args.steps, "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "samples": n, "rows_per_step": R, "level": LEVEL,
+                           "l2_policy": "inputs larger than L2: each step draws a new %d MB text window" % (
+                               text_bytes // len(stats) >> 20),
+                           "partition": "contiguous SNP ranges per rank, no collective"},
+                "e2e": {"value": e2e_calls / e2e_s, "unit": "calls/s", "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": d2h},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+                "compression_ratio": text_bytes / max(1, bgzf_bytes), "text_gb_per_s": text_bytes / (ms * 1e-3) / 1e9}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
