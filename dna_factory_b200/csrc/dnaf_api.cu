@@ -16,8 +16,11 @@
 
 #include "../../include/dnaf_b200.h"
 #include "dnaf_device.cuh"
+#include "fused_host.h"
 #include "k_deflate.cuh"
+#include "k_fused.cuh"
 #include "k_sample_format.cuh"
+#include <map>
 
 using namespace dnaf;
 
@@ -99,7 +102,8 @@ struct dnaf_ctx {
     uint64_t S = 0;
     bool any_multi = false;
     DevBuf d_cls, d_k, d_thr, d_prefix, d_pre_off, d_row_off;
-    std::vector<uint8_t> h_cls;
+    std::vector<uint8_t> h_cls, h_k;
+    std::vector<uint32_t> h_thr0;
     std::vector<uint32_t> h_plen;
     std::vector<uint64_t> h_row_off;  // valid when layout_ok
     bool layout_ok = false;
@@ -108,6 +112,7 @@ struct dnaf_ctx {
     uint64_t P = 0;
     DevBuf d_orow, d_osamp;
     std::vector<uint64_t> h_orow;
+    std::vector<uint32_t> h_osamp;
 
     // constant tables
     DevBuf d_crctab, d_xpow8;
@@ -119,6 +124,18 @@ struct dnaf_ctx {
 
     cudaEvent_t ev[8] = {};
     bool attr_done = false;
+
+    // fused path (k_fused.cuh): per-bucket static codes, CRC helper tables, per-segment template CRCs
+    bool fused_ok = false;
+    DevBuf d_ftables, d_etab, d_fdesc, d_gslot, d_grow, d_goff, d_olocal, d_osub;
+    std::vector<uint16_t> h_bucket;        // per row
+    std::vector<uint32_t> h_seg_crc;       // L(template body) per autosome segment index
+    std::vector<uint32_t> h_seg_cell0;     // first cell of every segment (+ end sentinel)
+    std::vector<FusedDesc> fplan;
+    std::vector<uint32_t> gslot, grow, olocal, osub;
+    std::vector<uint64_t> goff;
+    uint64_t gen_text_bytes = 0;
+    uint32_t pass_blocks = 0;
 };
 
 namespace {
@@ -170,6 +187,8 @@ SnpView snp_view(const dnaf_ctx* c) {
     return v;
 }
 
+void build_segments(dnaf_ctx* c);
+
 // Text offset of every row (prefix + class body), host and device copies.
 int ensure_layout(dnaf_ctx* c) {
     if (!c->have_samples || !c->have_snps) return fail(c, DNAF_E_ARG, "set_samples and set_snps must be called first");
@@ -183,43 +202,206 @@ int ensure_layout(dnaf_ctx* c) {
     c->h_row_off[c->S] = acc;
     int rc = upload(c, c->d_row_off, c->h_row_off.data(), c->S + 1);
     if (rc) return rc;
+    build_segments(c);
     c->layout_ok = true;
     return DNAF_OK;
 }
 
-inline uint32_t row_len(const dnaf_ctx* c, uint64_t r) { return (uint32_t)(c->h_row_off[r + 1] - c->h_row_off[r]); }
+// ------------------------------------------------------------------------------------------------
+// Fused-path set-up: MAF buckets -> static Huffman tables; CRC helper tables; template CRCs per segment.
+constexpr uint32_t kFusedMinRowBytes = 16384;  // shorter rows are packed several to a block by the generic path
 
-// BGZF block plan for rows [r0,r1); offsets relative to the text of row r0.  See k_deflate.cuh.
-void plan_blocks(dnaf_ctx* c, uint64_t r0, uint64_t r1) {
+uint32_t raw_crc(const uint8_t* p, size_t n, const uint32_t* tab) {
+    uint32_t c = 0;
+    for (size_t i = 0; i < n; ++i) c = tab[(c ^ p[i]) & 0xFFu] ^ (c >> 8);
+    return c;
+}
+
+int ensure_fused(dnaf_ctx* c, const uint8_t* kk, const uint32_t* thr, const uint8_t* prefix, const uint64_t* pre_off) {
+    c->fused_ok = false;
+    c->h_bucket.assign(c->S, 0);
+    if (c->S == 0) return DNAF_OK;
+    // bucket key: the first threshold (minor-allele probability = 1 - (T+1)/2^32), coarsened until <= 512 keys
+    std::map<uint32_t, int> keys;
+    int shift = 0;
+    for (;; shift += 2) {
+        keys.clear();
+        bool ok = true;
+        for (uint64_t r = 0; r < c->S && ok; ++r) {
+            const uint32_t t = kk[r] >= 2 ? thr[r * 4] : 0xFFFFFFFFu;
+            keys.emplace(t >> shift, 0);
+            ok = keys.size() <= 512;
+        }
+        if (ok) break;
+    }
+    int nb = 0;
+    for (auto& kv : keys) kv.second = nb++;
+    for (uint64_t r = 0; r < c->S; ++r) {
+        const uint32_t t = kk[r] >= 2 ? thr[r * 4] : 0xFFFFFFFFu;
+        c->h_bucket[r] = (uint16_t)keys[t >> shift];
+    }
+    // prefix byte statistics (per row, x16 fixed point)
+    std::vector<uint64_t> ph(256, 0);
+    const uint64_t total = pre_off[c->S];
+    for (uint64_t i = 0; i < total; ++i) ph[prefix[i]]++;
+    for (auto& v : ph)
+        if (v) v = std::max<uint64_t>(1, (v * 16 + c->S / 2) / c->S);
+    std::vector<FusedTable> tabs((size_t)nb * 2);
+    for (auto& kv : keys) {
+        const uint64_t lo = (uint64_t)kv.first << shift;
+        const uint64_t hi = std::min<uint64_t>(0xFFFFFFFFull, lo + ((1ull << shift) - 1));
+        const double t_mid = 0.5 * ((double)lo + (double)hi);
+        const double p_minor = std::min(1.0, std::max(0.0, 1.0 - (t_mid + 1.0) / 4294967296.0));
+        tabs[2 * kv.second] = hosttab::make_table(p_minor, ph.data());      // segments that carry the row prefix
+        tabs[2 * kv.second + 1] = hosttab::make_table(p_minor, nullptr);    // the others
+        if (tabs[2 * kv.second].hdr_bits == 0xFFFFFFFFu || tabs[2 * kv.second + 1].hdr_bits == 0xFFFFFFFFu) return DNAF_OK;
+    }
+    int rc = upload(c, c->d_ftables, tabs.data(), tabs.size());
+    if (rc) return rc;
+    // E tables: contribution of mask byte b at byte k of word w to the span's linear CRC (span end aligned)
+    std::vector<uint32_t> tab(256), xp(257);
+    for (uint32_t i = 0; i < 256; ++i) {
+        uint32_t v = i;
+        for (int k = 0; k < 8; ++k) v = (v & 1u) ? (v >> 1) ^ kCrcPoly : (v >> 1);
+        tab[i] = v;
+    }
+    xp[0] = 0x80000000u;
+    for (int k = 1; k <= 256; ++k) xp[k] = hosttab::mulmod(xp[k - 1], 0x00800000u);
+    std::vector<uint32_t> etab(16 * 256, 0);
+    for (int w = 0; w < 4; ++w)
+        for (int k = 0; k < 4; ++k)
+            for (int b = 0; b < 256; ++b) {
+                uint32_t v = 0;
+                for (int i = 0; i < 8; ++i)
+                    if ((b >> i) & 1) {
+                        const int j = 32 * w + 8 * k + i;             // allele slot, byte 2j of the span
+                        v ^= hosttab::mulmod(xp[255 - 2 * j], tab[1]);
+                    }
+                etab[(4 * w + k) * 256 + b] = v;
+            }
+    rc = upload(c, c->d_etab, etab.data(), etab.size());
+    if (rc) return rc;
+    c->fused_ok = true;
+    return DNAF_OK;
+}
+
+// Segments of an autosome row and the linear CRC of their all-reference template bodies.
+void build_segments(dnaf_ctx* c) {
+    c->h_seg_cell0.clear();
+    c->h_seg_crc.clear();
+    if (c->n == 0) return;
+    std::vector<uint32_t> tab(256);
+    for (uint32_t i = 0; i < 256; ++i) {
+        uint32_t v = i;
+        for (int k = 0; k < 8; ++k) v = (v & 1u) ? (v >> 1) ^ kCrcPoly : (v >> 1);
+        tab[i] = v;
+    }
+    std::vector<uint8_t> body((size_t)4 * c->n);
+    for (uint32_t i = 0; i < c->n; ++i) memcpy(&body[4ull * i], "0/0\t", 4);
+    body.back() = '\n';
+    uint32_t cell = 0;
+    bool first = true;
+    while (cell < c->n) {
+        const uint32_t cap = (first ? 254u : 255u) * 64u;
+        const uint32_t cnt = std::min(cap, c->n - cell);
+        c->h_seg_cell0.push_back(cell);
+        c->h_seg_crc.push_back(raw_crc(&body[4ull * cell], 4ull * cnt, tab.data()));
+        cell += cnt;
+        first = false;
+    }
+    c->h_seg_cell0.push_back(c->n);
+}
+
+inline bool row_is_fused(const dnaf_ctx* c, uint64_t r, const uint8_t* hk) {
+    return c->fused && c->fused_ok && c->h_cls[r] == kAuto && hk[r] <= 2 && c->h_plen[r] >= 1 && c->h_plen[r] <= 256 &&
+           4ull * c->n >= kFusedMinRowBytes;
+}
+
+// BGZF block plan of one pass (rows [r0,r1)): fused segments and generic blocks, slots in row order.
+void plan_pass(dnaf_ctx* c, uint64_t r0, uint64_t r1, const uint8_t* hk) {
+    c->fplan.clear();
     c->plan.clear();
-    const uint64_t text0 = c->h_row_off[r0];
+    c->gslot.clear();
+    c->grow.clear();
+    c->goff.clear();
+    c->olocal.clear();
+    c->osub.clear();
+    uint64_t gtext = 0;
+    uint32_t slot = 0;
+    size_t o = std::lower_bound(c->h_orow.begin(), c->h_orow.end(), r0) - c->h_orow.begin();
     uint64_t r = r0;
     while (r < r1) {
-        const uint64_t off = c->h_row_off[r] - text0;
-        const uint64_t len = c->h_row_off[r + 1] - c->h_row_off[r];
-        const uint32_t plen = c->h_plen[r];
-        if (len > kBlk) {
-            uint64_t done = 0;
-            if (plen + kSpan <= kBlk) {  // first segment: prefix + whole 256-byte spans of the body
-                const uint64_t first = plen + (uint64_t)((kBlk - plen) / kSpan) * kSpan;
-                c->plan.push_back({off, (uint32_t)std::min<uint64_t>(first, len), plen});
-                done = std::min<uint64_t>(first, len);
+        while (o < c->h_orow.size() && c->h_orow[o] < r) ++o;
+        if (row_is_fused(c, r, hk)) {
+            size_t oe = o;
+            while (oe < c->h_orow.size() && c->h_orow[oe] == r) ++oe;
+            const size_t nseg = c->h_seg_crc.size();
+            for (size_t sgi = 0; sgi < nseg; ++sgi) {
+                FusedDesc d;
+                d.row = r;
+                d.cell0 = c->h_seg_cell0[sgi];
+                d.ncells = c->h_seg_cell0[sgi + 1] - d.cell0;
+                d.slot = slot++;
+                d.flags = (sgi == 0 ? 1u : 0u) | (sgi + 1 == nseg ? 2u : 0u);
+                d.ovr_first = (uint32_t)o;
+                d.ovr_count = (uint32_t)(oe - o);
+                d.table = 2u * c->h_bucket[r] + (sgi == 0 ? 0u : 1u);
+                d.body_crc = c->h_seg_crc[sgi];
+                c->fplan.push_back(d);
             }
-            while (done < len) {
-                const uint32_t piece = (uint32_t)std::min<uint64_t>(kBlk, len - done);
-                c->plan.push_back({off + done, piece, 0});
-                done += piece;
-            }
+            o = oe;
             ++r;
-        } else {
-            uint64_t acc = 0;
-            while (r < r1 && acc + (c->h_row_off[r + 1] - c->h_row_off[r]) <= kBlk) {
-                acc += c->h_row_off[r + 1] - c->h_row_off[r];
-                ++r;
+            continue;
+        }
+        // a run of consecutive generic rows: text laid out back to back in the generic text buffer
+        const uint64_t run_begin = r;
+        while (r < r1 && !row_is_fused(c, r, hk)) {
+            c->grow.push_back((uint32_t)(r - r0));
+            c->goff.push_back(gtext);
+            while (o < c->h_orow.size() && c->h_orow[o] == r) {
+                c->olocal.push_back((uint32_t)(c->grow.size() - 1));
+                c->osub.push_back(c->h_osamp[o]);
+                ++o;
             }
-            c->plan.push_back({off, (uint32_t)acc, std::min<uint32_t>(plen, (uint32_t)acc)});
+            gtext += c->h_row_off[r + 1] - c->h_row_off[r];
+            ++r;
+        }
+        uint64_t q = run_begin;
+        size_t gi = c->grow.size() - (size_t)(r - run_begin);
+        while (q < r) {
+            const uint64_t off = c->goff[gi];
+            const uint64_t len = c->h_row_off[q + 1] - c->h_row_off[q];
+            const uint32_t plen = c->h_plen[q];
+            if (len > kBlk) {
+                uint64_t done = 0;
+                if (plen + kSpan <= kBlk) {
+                    const uint64_t first = plen + (uint64_t)((kBlk - plen) / kSpan) * kSpan;
+                    c->plan.push_back({off, (uint32_t)std::min<uint64_t>(first, len), plen});
+                    c->gslot.push_back(slot++);
+                    done = std::min<uint64_t>(first, len);
+                }
+                while (done < len) {
+                    const uint32_t piece = (uint32_t)std::min<uint64_t>(kBlk, len - done);
+                    c->plan.push_back({off + done, piece, 0});
+                    c->gslot.push_back(slot++);
+                    done += piece;
+                }
+                ++q;
+                ++gi;
+            } else {
+                uint64_t acc = 0;
+                while (q < r && acc + (c->h_row_off[q + 1] - c->h_row_off[q]) <= kBlk) {
+                    acc += c->h_row_off[q + 1] - c->h_row_off[q];
+                    ++q;
+                    ++gi;
+                }
+                c->plan.push_back({off, (uint32_t)acc, std::min<uint32_t>(plen, (uint32_t)acc)});
+                c->gslot.push_back(slot++);
+            }
         }
     }
+    c->gen_text_bytes = gtext;
+    c->pass_blocks = slot;
 }
 
 struct Sink {
@@ -242,14 +424,14 @@ int deliver(dnaf_ctx* c, Sink& s, const uint8_t* data, uint64_t n) {
     return DNAF_OK;
 }
 
-// Encode the blocks in c->plan from d_text, compact, and hand the bytes to the sink.
-int encode_plan(dnaf_ctx* c, Sink& sink, dnaf_stats* st, cudaEvent_t ev_begin, cudaEvent_t ev_end) {
-    const uint32_t nb = (uint32_t)c->plan.size();
-    if (nb == 0) return DNAF_OK;
-    CU(c, c->d_blocks.reserve(nb * sizeof(BlockDesc)));
-    CU(c, c->h_blocks.reserve(nb * sizeof(BlockDesc)));
-    memcpy(c->h_blocks.p, c->plan.data(), nb * sizeof(BlockDesc));
-    CU(c, cudaMemcpyAsync(c->d_blocks.p, c->h_blocks.p, nb * sizeof(BlockDesc), cudaMemcpyHostToDevice, c->stream));
+template <class T>
+int upload_async(dnaf_ctx* c, DevBuf& b, const std::vector<T>& v) {
+    CU(c, b.reserve(std::max<size_t>(v.size(), 1) * sizeof(T)));
+    if (!v.empty()) CU(c, cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    return DNAF_OK;
+}
+
+int reserve_outputs(dnaf_ctx* c, uint32_t nb) {
     CU(c, c->d_slots.reserve((size_t)nb * kSlot));
     CU(c, c->d_sizes.reserve(nb * sizeof(uint32_t)));
     CU(c, c->d_crcs.reserve(nb * sizeof(uint32_t)));
@@ -261,29 +443,42 @@ int encode_plan(dnaf_ctx* c, Sink& sink, dnaf_stats* st, cudaEvent_t ev_begin, c
         CU(c, cudaFuncSetAttribute(k_bgzf_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DeflateSmem)));
         c->attr_done = true;
     }
-    CU(c, cudaEventRecord(ev_begin, c->stream));
-    k_bgzf_generic<<<nb, 256, sizeof(DeflateSmem), c->stream>>>(c->d_text.as<uint8_t>(), c->d_blocks.as<BlockDesc>(),
-                                                               c->d_crctab.as<uint32_t>(), c->d_xpow8.as<uint32_t>(),
-                                                               c->d_slots.as<uint8_t>(), c->d_sizes.as<uint32_t>(),
-                                                               c->d_crcs.as<uint32_t>());
+    return DNAF_OK;
+}
+
+// generic encoder over c->plan (text in d_text), slots from c->gslot (or 0..n-1 when empty)
+int launch_generic(dnaf_ctx* c, dnaf_stats* st) {
+    const uint32_t nb = (uint32_t)c->plan.size();
+    if (!nb) return DNAF_OK;
+    int rc = upload_async(c, c->d_blocks, c->plan);
+    if (!rc) rc = upload_async(c, c->d_gslot, c->gslot);
+    if (rc) return rc;
+    k_bgzf_generic<<<nb, 256, sizeof(DeflateSmem), c->stream>>>(
+        c->d_text.as<uint8_t>(), c->d_blocks.as<BlockDesc>(), c->gslot.empty() ? nullptr : c->d_gslot.as<uint32_t>(),
+        c->d_crctab.as<uint32_t>(), c->d_xpow8.as<uint32_t>(), c->d_slots.as<uint8_t>(), c->d_sizes.as<uint32_t>(),
+        c->d_crcs.as<uint32_t>());
+    if (st) st->kernel_launches += 1;
+    CU(c, cudaGetLastError());
+    return DNAF_OK;
+}
+
+// scan + compact the first nb slots, then hand the bytes to the sink
+int finish_pass(dnaf_ctx* c, uint32_t nb, Sink& sink, dnaf_stats* st) {
+    if (!nb) return DNAF_OK;
     k_scan_sizes<<<1, 1024, 0, c->stream>>>(c->d_sizes.as<uint32_t>(), nb, c->d_offsets.as<uint64_t>(),
                                             c->d_crcs.as<uint32_t>(), c->d_totals.as<uint64_t>());
     k_compact<<<nb, 256, 0, c->stream>>>(c->d_slots.as<uint8_t>(), kSlot, c->d_sizes.as<uint32_t>(),
                                          c->d_offsets.as<uint64_t>(), c->d_out.as<uint8_t>());
-    CU(c, cudaEventRecord(ev_end, c->stream));
+    CU(c, cudaEventRecord(c->ev[5], c->stream));
     CU(c, cudaGetLastError());
     CU(c, cudaMemcpyAsync(c->h_totals.p, c->d_totals.p, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     const uint64_t bytes = c->h_totals.as<uint64_t>()[0];
-    const uint32_t cx = (uint32_t)c->h_totals.as<uint64_t>()[1];
     if (st) {
         st->bgzf_bytes += bytes;
         st->bgzf_blocks += nb;
-        st->crc_xor ^= cx;
-        st->kernel_launches += 3;
-        float ms = 0;
-        cudaEventElapsedTime(&ms, ev_begin, ev_end);
-        st->ms_deflate += ms;
+        st->crc_xor ^= (uint32_t)c->h_totals.as<uint64_t>()[1];
+        st->kernel_launches += 2;
     }
     if (!sink.device_only) {
         CU(c, c->h_out.reserve(bytes));
@@ -295,25 +490,22 @@ int encode_plan(dnaf_ctx* c, Sink& sink, dnaf_stats* st, cudaEvent_t ev_begin, c
     return DNAF_OK;
 }
 
-// sample (+ overrides) for rows [r0,r1) into the plane buffers
-int run_sample(dnaf_ctx* c, uint64_t r0, uint64_t r1, uint64_t seed, dnaf_stats* st) {
+// sample (+ overrides) `rows` rows into the plane buffers; row list optional (d_grow), overrides as local pairs
+int run_sample(dnaf_ctx* c, uint64_t r0, uint32_t rows, const uint32_t* d_row_idx, uint64_t seed, uint64_t n_over,
+               const uint32_t* d_olocal, const uint32_t* d_osamp, dnaf_stats* st) {
     const SampleView sv = sample_view(c);
-    const uint32_t rows = (uint32_t)(r1 - r0);
     const uint64_t words = (uint64_t)rows * sv.groups;
     CU(c, c->d_plane0.reserve(std::max<uint64_t>(words, 1) * 4));
     if (c->any_multi) CU(c, c->d_plane1.reserve(std::max<uint64_t>(words, 1) * 4));
     uint32_t* p1 = c->any_multi ? c->d_plane1.as<uint32_t>() : nullptr;
     if (words) {
         const uint32_t grid = (uint32_t)((words + 255) / 256);
-        k_sample<<<grid, 256, 0, c->stream>>>(sv, snp_view(c), r0, c->row_base, rows, (uint32_t)seed, (uint32_t)(seed >> 32),
-                                              c->d_plane0.as<uint32_t>(), p1);
+        k_sample<<<grid, 256, 0, c->stream>>>(sv, snp_view(c), r0, d_row_idx, c->row_base, rows, (uint32_t)seed,
+                                              (uint32_t)(seed >> 32), c->d_plane0.as<uint32_t>(), p1);
         if (st) st->kernel_launches += 1;
-        const uint64_t o0 = std::lower_bound(c->h_orow.begin(), c->h_orow.end(), r0) - c->h_orow.begin();
-        const uint64_t o1 = std::lower_bound(c->h_orow.begin(), c->h_orow.end(), r1) - c->h_orow.begin();
-        if (o1 > o0) {
-            k_overrides<<<(uint32_t)((o1 - o0 + 255) / 256), 256, 0, c->stream>>>(
-                c->d_orow.as<uint64_t>(), c->d_osamp.as<uint32_t>(), o0, o1 - o0, r0, sv.groups, c->n,
-                c->d_plane0.as<uint32_t>(), p1);
+        if (n_over) {
+            k_overrides<<<(uint32_t)((n_over + 255) / 256), 256, 0, c->stream>>>(d_olocal, d_osamp, n_over, sv.groups, c->n,
+                                                                              c->d_plane0.as<uint32_t>(), p1);
             if (st) st->kernel_launches += 1;
         }
     }
@@ -321,13 +513,34 @@ int run_sample(dnaf_ctx* c, uint64_t r0, uint64_t r1, uint64_t seed, dnaf_stats*
     return DNAF_OK;
 }
 
-int run_format(dnaf_ctx* c, uint64_t r0, uint64_t r1, dnaf_stats* st) {
-    const uint64_t text0 = c->h_row_off[r0];
-    const uint64_t bytes = c->h_row_off[r1] - text0;
-    CU(c, c->d_text.reserve(bytes + 64));
-    const uint32_t rows = (uint32_t)(r1 - r0);
-    k_format<<<rows, 256, 0, c->stream>>>(sample_view(c), snp_view(c), r0, c->d_row_off.as<uint64_t>(), text0,
-                                          c->d_plane0.as<uint32_t>(),
+// overrides of rows [r0,r1) as (local row, sample) device arrays (all rows, no subset)
+int stage_overrides_all(dnaf_ctx* c, uint64_t r0, uint64_t r1, uint64_t* n_over) {
+    const size_t o0 = std::lower_bound(c->h_orow.begin(), c->h_orow.end(), r0) - c->h_orow.begin();
+    const size_t o1 = std::lower_bound(c->h_orow.begin(), c->h_orow.end(), r1) - c->h_orow.begin();
+    c->olocal.clear();
+    c->osub.clear();
+    for (size_t o = o0; o < o1; ++o) {
+        c->olocal.push_back((uint32_t)(c->h_orow[o] - r0));
+        c->osub.push_back(c->h_osamp[o]);
+    }
+    *n_over = o1 - o0;
+    return DNAF_OK;
+}
+
+// uploads the (local row, sample) override pairs staged in c->olocal / c->osub
+int upload_overrides(dnaf_ctx* c) {
+    if (c->olocal.empty()) return DNAF_OK;
+    int rc = upload_async(c, c->d_olocal, c->olocal);
+    if (!rc) rc = upload_async(c, c->d_osub, c->osub);
+    return rc;
+}
+
+int run_format(dnaf_ctx* c, uint64_t r0, uint32_t rows, const uint32_t* d_row_idx, const uint64_t* d_sub_off,
+               uint64_t text_bytes, dnaf_stats* st) {
+    CU(c, c->d_text.reserve(text_bytes + 64));
+    if (!rows) return DNAF_OK;
+    k_format<<<rows, 256, 0, c->stream>>>(sample_view(c), snp_view(c), r0, d_row_idx, d_sub_off,
+                                          c->d_row_off.as<uint64_t>(), c->h_row_off[r0], c->d_plane0.as<uint32_t>(),
                                           c->any_multi ? c->d_plane1.as<uint32_t>() : nullptr, c->d_text.as<uint8_t>());
     if (st) st->kernel_launches += 1;
     CU(c, cudaGetLastError());
@@ -356,23 +569,68 @@ int generate_impl(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t se
     uint64_t r0 = row_begin;
     while (r0 < row_end) {
         const uint64_t r1 = next_chunk_end(c, r0, row_end, c->chunk_bytes);
+        plan_pass(c, r0, r1, c->h_k.data());
+        rc = reserve_outputs(c, c->pass_blocks);
+        if (rc) return rc;
         CU(c, cudaEventRecord(c->ev[0], c->stream));
-        rc = run_sample(c, r0, r1, seed, &local);
-        if (rc) return rc;
+        const uint32_t grows = (uint32_t)c->grow.size();
+        if (grows) {
+            rc = upload_async(c, c->d_grow, c->grow);
+            if (!rc) rc = upload_async(c, c->d_goff, c->goff);
+            if (!rc) rc = upload_overrides(c);
+            if (!rc) rc = run_sample(c, r0, grows, c->d_grow.as<uint32_t>(), seed, c->olocal.size(),
+                                     c->d_olocal.as<uint32_t>(), c->d_osub.as<uint32_t>(), &local);
+            if (rc) return rc;
+        }
         CU(c, cudaEventRecord(c->ev[1], c->stream));
-        rc = run_format(c, r0, r1, &local);
-        if (rc) return rc;
+        if (grows) {
+            rc = run_format(c, r0, grows, c->d_grow.as<uint32_t>(), c->d_goff.as<uint64_t>(), c->gen_text_bytes, &local);
+            if (rc) return rc;
+        }
         CU(c, cudaEventRecord(c->ev[2], c->stream));
-        plan_blocks(c, r0, r1);
-        rc = encode_plan(c, sink, &local, c->ev[3], c->ev[4]);
+        rc = launch_generic(c, &local);
         if (rc) return rc;
-        float a = 0, b = 0, t = 0;
-        cudaEventElapsedTime(&a, c->ev[0], c->ev[1]);
-        cudaEventElapsedTime(&b, c->ev[1], c->ev[2]);
-        cudaEventElapsedTime(&t, c->ev[0], c->ev[4]);
-        local.ms_sample += a;
-        local.ms_format += b;
-        local.ms_total += t;
+        CU(c, cudaEventRecord(c->ev[3], c->stream));
+        if (!c->fplan.empty()) {
+            rc = upload_async(c, c->d_fdesc, c->fplan);
+            if (rc) return rc;
+            FusedArgs fa;
+            fa.sv = sample_view(c);
+            fa.nv = snp_view(c);
+            fa.desc = c->d_fdesc.as<FusedDesc>();
+            fa.tables = c->d_ftables.as<FusedTable>();
+            fa.etab = c->d_etab.as<uint32_t>();
+            fa.crctab = c->d_crctab.as<uint32_t>();
+            fa.xpow8 = c->d_xpow8.as<uint32_t>();
+            fa.orow = c->d_orow.as<uint64_t>();
+            fa.osamp = c->d_osamp.as<uint32_t>();
+            fa.row_base = c->row_base;
+            fa.k0 = (uint32_t)seed;
+            fa.k1 = (uint32_t)(seed >> 32);
+            fa.slots = c->d_slots.as<uint8_t>();
+            fa.sizes = c->d_sizes.as<uint32_t>();
+            fa.crcs = c->d_crcs.as<uint32_t>();
+            k_fused_auto<<<(uint32_t)c->fplan.size(), kFusedThreads, 0, c->stream>>>(fa);
+            local.kernel_launches += 1;
+            CU(c, cudaGetLastError());
+        }
+        CU(c, cudaEventRecord(c->ev[4], c->stream));
+        rc = finish_pass(c, c->pass_blocks, sink, &local);
+        if (rc) return rc;
+        float t01 = 0, t12 = 0, t23 = 0, t34 = 0, t45 = 0, t05 = 0;
+        cudaEventElapsedTime(&t01, c->ev[0], c->ev[1]);
+        cudaEventElapsedTime(&t12, c->ev[1], c->ev[2]);
+        cudaEventElapsedTime(&t23, c->ev[2], c->ev[3]);
+        cudaEventElapsedTime(&t34, c->ev[3], c->ev[4]);
+        cudaEventElapsedTime(&t45, c->ev[4], c->ev[5]);
+        cudaEventElapsedTime(&t05, c->ev[0], c->ev[5]);
+        if (grows) {
+            local.ms_sample += t01;
+            local.ms_format += t12;
+        }
+        local.ms_deflate += (c->plan.empty() ? 0.f : t23) + t45;
+        if (!c->fplan.empty()) local.ms_fused += t34;
+        local.ms_total += t05;
         local.rows += r1 - r0;
         local.text_bytes += c->h_row_off[r1] - c->h_row_off[r0];
         r0 = r1;
@@ -522,6 +780,7 @@ int dnaf_set_snps(dnaf_ctx* c, uint64_t S, const uint8_t* cls, const uint8_t* k,
     c->S = S;
     c->any_multi = multi;
     c->h_cls.assign(cls, cls + S);
+    c->h_k.assign(k, k + S);
     c->h_plen.resize(S);
     for (uint64_t r = 0; r < S; ++r) c->h_plen[r] = (uint32_t)(pre_off[r + 1] - pre_off[r]);
     int rc = upload(c, c->d_cls, cls, S);
@@ -537,6 +796,8 @@ int dnaf_set_snps(dnaf_ctx* c, uint64_t S, const uint8_t* cls, const uint8_t* k,
     }
     c->have_snps = true;
     c->layout_ok = false;
+    rc = ensure_fused(c, k, thr, prefix, pre_off);
+    if (rc) return rc;
     return DNAF_OK;
 }
 
@@ -547,6 +808,7 @@ int dnaf_set_overrides(dnaf_ctx* c, uint64_t P, const uint64_t* rows, const uint
         if (rows[i] < rows[i - 1]) return fail(c, DNAF_E_ARG, "override pairs must be sorted by row");
     CU(c, cudaSetDevice(c->dev));
     c->h_orow.assign(rows, rows + P);
+    c->h_osamp.assign(samples, samples + P);
     int rc = upload(c, c->d_orow, rows, P);
     if (!rc) rc = upload(c, c->d_osamp, samples, P);
     if (rc) return rc;
@@ -621,7 +883,11 @@ int dnaf_genotypes(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t s
     const uint64_t rows_per = std::max<uint64_t>(1, (64ull << 20) / (2ull * c->n));
     for (uint64_t r0 = row_begin; r0 < row_end; r0 += rows_per) {
         const uint64_t r1 = std::min(row_end, r0 + rows_per);
-        rc = run_sample(c, r0, r1, seed, nullptr);
+        uint64_t n_over = 0;
+        stage_overrides_all(c, r0, r1, &n_over);
+        rc = upload_overrides(c);
+        if (!rc) rc = run_sample(c, r0, (uint32_t)(r1 - r0), nullptr, seed, n_over, c->d_olocal.as<uint32_t>(),
+                                 c->d_osub.as<uint32_t>(), nullptr);
         if (rc) return rc;
         const uint64_t cells = (r1 - r0) * c->n;
         CU(c, c->d_geno.reserve(cells * 2));
@@ -651,10 +917,14 @@ int dnaf_text(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t seed, 
     uint64_t r0 = row_begin, done = 0;
     while (r0 < row_end) {
         const uint64_t r1 = next_chunk_end(c, r0, row_end, c->chunk_bytes);
-        rc = run_sample(c, r0, r1, seed, nullptr);
-        if (!rc) rc = run_format(c, r0, r1, nullptr);
-        if (rc) return rc;
         const uint64_t bytes = c->h_row_off[r1] - c->h_row_off[r0];
+        uint64_t n_over = 0;
+        stage_overrides_all(c, r0, r1, &n_over);
+        rc = upload_overrides(c);
+        if (!rc) rc = run_sample(c, r0, (uint32_t)(r1 - r0), nullptr, seed, n_over, c->d_olocal.as<uint32_t>(),
+                                 c->d_osub.as<uint32_t>(), nullptr);
+        if (!rc) rc = run_format(c, r0, (uint32_t)(r1 - r0), nullptr, nullptr, bytes, nullptr);
+        if (rc) return rc;
         CU(c, cudaMemcpyAsync(out + done, c->d_text.p, bytes, cudaMemcpyDeviceToHost, c->stream));
         CU(c, cudaStreamSynchronize(c->stream));
         done += bytes;
@@ -680,10 +950,18 @@ int dnaf_bgzf_compress(dnaf_ctx* c, const uint8_t* text, uint64_t n, int level, 
         CU(c, c->d_text.reserve(piece + 64));
         CU(c, cudaMemcpyAsync(c->d_text.p, text + done, piece, cudaMemcpyHostToDevice, c->stream));
         c->plan.clear();
+        c->gslot.clear();
         for (uint64_t o = 0; o < piece; o += kBlk)
             c->plan.push_back({o, (uint32_t)std::min<uint64_t>(kBlk, piece - o), 0});
-        int rc = encode_plan(c, s, &local, c->ev[3], c->ev[4]);
+        int rc = reserve_outputs(c, (uint32_t)c->plan.size());
         if (rc) return rc;
+        CU(c, cudaEventRecord(c->ev[0], c->stream));
+        rc = launch_generic(c, &local);
+        if (!rc) rc = finish_pass(c, (uint32_t)c->plan.size(), s, &local);
+        if (rc) return rc;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->ev[0], c->ev[5]);
+        local.ms_deflate += ms;
         local.text_bytes += piece;
         done += piece;
     }

@@ -1,0 +1,233 @@
+// Host-side set-up for the fused kernel: static Huffman codes per minor-allele-frequency bucket, their
+// serialized deflate dynamic-block headers, and the CRC tables the mask-domain checksum needs.
+//
+// The codes are built from token statistics obtained by running the kernel's own tokeniser
+// (tokenize_cells, k_fused.cuh) over Bernoulli(maf) masks from a fixed-seed generator, which is the model
+// the reference's row loop samples from (pop_factory.py:477-494).  Every symbol a block can need gets a
+// code (add-one smoothing), so any mask pattern -- including forced-minor cells -- stays encodable.
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <queue>
+#include <vector>
+
+#include "k_fused.cuh"
+
+namespace dnaf {
+namespace hosttab {
+
+inline uint32_t mulmod(uint32_t a, uint32_t b) {
+    uint32_t p = 0;
+    for (int i = 0; i < 32; ++i) {
+        if (a & 0x80000000u) p ^= b;
+        a <<= 1;
+        b = (b & 1u) ? (b >> 1) ^ kCrcPoly : (b >> 1);
+    }
+    return p;
+}
+
+inline int len_index(int len) {
+    static const int base[29] = {3,  4,  5,  6,  7,  8,  9,  10, 11,  13,  15,  17,  19,  23, 27,
+                                 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+    for (int i = 28; i >= 0; --i)
+        if (len >= base[i]) return i;
+    return 0;
+}
+static const int kLenBase[29] = {3,  4,  5,  6,  7,  8,  9,  10, 11,  13,  15,  17,  19,  23, 27,
+                                 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+static const int kLenExtra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+
+// Huffman code lengths limited to maxbits (frequencies are halved until the tree is shallow enough).
+inline std::vector<uint8_t> huff_lengths(const std::vector<uint64_t>& freq_in, int maxbits) {
+    const int n = (int)freq_in.size();
+    std::vector<uint8_t> lens(n, 0);
+    std::vector<int> used;
+    for (int i = 0; i < n; ++i)
+        if (freq_in[i]) used.push_back(i);
+    if (used.empty()) return lens;
+    if (used.size() == 1) {
+        lens[used[0]] = 1;
+        return lens;
+    }
+    for (int shift = 0;; ++shift) {
+        struct Node { uint64_t w; int id; };
+        auto cmp = [](const Node& a, const Node& b) { return a.w > b.w || (a.w == b.w && a.id > b.id); };
+        std::priority_queue<Node, std::vector<Node>, decltype(cmp)> pq(cmp);
+        std::vector<int> parent(2 * used.size(), -1);
+        for (size_t i = 0; i < used.size(); ++i) pq.push({std::max<uint64_t>(1, freq_in[used[i]] >> shift), (int)i});
+        int next = (int)used.size();
+        while (pq.size() > 1) {
+            Node a = pq.top(); pq.pop();
+            Node b = pq.top(); pq.pop();
+            parent[a.id] = next;
+            parent[b.id] = next;
+            pq.push({a.w + b.w, next});
+            ++next;
+        }
+        int maxd = 0;
+        std::vector<int> depth(used.size());
+        for (size_t i = 0; i < used.size(); ++i) {
+            int d = 0;
+            for (int v = (int)i; parent[v] >= 0; v = parent[v]) ++d;
+            depth[i] = d;
+            maxd = std::max(maxd, d);
+        }
+        if (maxd <= maxbits) {
+            for (size_t i = 0; i < used.size(); ++i) lens[used[i]] = (uint8_t)depth[i];
+            return lens;
+        }
+    }
+}
+
+inline uint32_t reverse_bits(uint32_t code, int len) {
+    uint32_t r = 0;
+    for (int i = 0; i < len; ++i) r |= ((code >> i) & 1u) << (len - 1 - i);
+    return r;
+}
+
+// canonical codes, bit-reversed; out[i] = code | len << 24
+inline std::vector<uint32_t> huff_codes(const std::vector<uint8_t>& lens) {
+    uint32_t count[16] = {0}, next[16] = {0};
+    for (uint8_t l : lens) count[l]++;
+    count[0] = 0;
+    uint32_t code = 0;
+    for (int b = 1; b < 16; ++b) {
+        code = (code + count[b - 1]) << 1;
+        next[b] = code;
+    }
+    std::vector<uint32_t> out(lens.size(), 0);
+    for (size_t i = 0; i < lens.size(); ++i)
+        if (lens[i]) out[i] = reverse_bits(next[lens[i]]++, lens[i]) | ((uint32_t)lens[i] << 24);
+    return out;
+}
+
+struct BitString {
+    std::vector<uint32_t> words;
+    uint32_t bits = 0;
+    void put(uint32_t v, int n) {
+        for (int i = 0; i < n; ++i, ++bits) {
+            if ((bits >> 5) >= words.size()) words.push_back(0);
+            if ((v >> i) & 1u) words[bits >> 5] |= 1u << (bits & 31);
+        }
+    }
+};
+
+// BFINAL=1, BTYPE=2 header for literal/length lengths `ll` (286) and the single distance code 3.
+inline BitString dynamic_header(const std::vector<uint8_t>& ll) {
+    static const int order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+    int nlit = 286;
+    while (nlit > 257 && ll[nlit - 1] == 0) --nlit;
+    std::vector<uint8_t> seq(ll.begin(), ll.begin() + nlit);
+    const uint8_t dist[4] = {0, 0, 0, 1};
+    seq.insert(seq.end(), dist, dist + 4);
+    std::vector<std::pair<int, int>> rl;  // (symbol, extra)
+    for (size_t i = 0; i < seq.size();) {
+        const int v = seq[i];
+        size_t run = 1;
+        while (i + run < seq.size() && seq[i + run] == v) ++run;
+        i += run;
+        if (v == 0) {
+            while (run >= 11) { const size_t c = std::min<size_t>(run, 138); rl.push_back({18, (int)c - 11}); run -= c; }
+            if (run >= 3) { rl.push_back({17, (int)run - 3}); run = 0; }
+            while (run-- > 0) rl.push_back({0, 0});
+        } else {
+            rl.push_back({v, 0});
+            --run;
+            while (run >= 3) { const size_t c = std::min<size_t>(run, 6); rl.push_back({16, (int)c - 3}); run -= c; }
+            while (run-- > 0) rl.push_back({v, 0});
+        }
+    }
+    std::vector<uint64_t> clf(19, 0);
+    for (auto& p : rl) clf[p.first]++;
+    std::vector<uint8_t> cll = huff_lengths(clf, 7);
+    int used = 0, only = 0;
+    for (int i = 0; i < 19; ++i)
+        if (cll[i]) { ++used; only = i; }
+    if (used == 1) cll[only == 0 ? 1 : 0] = 1;
+    std::vector<uint32_t> clc = huff_codes(cll);
+    int ncl = 19;
+    while (ncl > 4 && cll[order[ncl - 1]] == 0) --ncl;
+    BitString bs;
+    bs.put(1, 1);
+    bs.put(2, 2);
+    bs.put(nlit - 257, 5);
+    bs.put(4 - 1, 5);
+    bs.put(ncl - 4, 4);
+    for (int i = 0; i < ncl; ++i) bs.put(cll[order[i]], 3);
+    for (auto& p : rl) {
+        bs.put(clc[p.first] & 0xFFFFFFu, (int)(clc[p.first] >> 24));
+        if (p.first == 16) bs.put(p.second, 2);
+        else if (p.first == 17) bs.put(p.second, 3);
+        else if (p.first == 18) bs.put(p.second, 7);
+    }
+    return bs;
+}
+
+struct HistSink {
+    uint64_t nlit[8] = {0};
+    uint64_t nlen[29] = {0};
+    void lit(int id) { nlit[id]++; }
+    void match(int l) { nlen[len_index(l)]++; }
+};
+
+// Token statistics of `blocks` full segments (255 spans of 64 cells) of Bernoulli(p_minor) alleles.
+inline HistSink simulate(double p_minor, int blocks) {
+    HistSink h;
+    uint64_t st = 0x9E3779B97F4A7C15ull ^ (uint64_t)(p_minor * 1e9);
+    auto next = [&]() {
+        st ^= st << 13; st ^= st >> 7; st ^= st << 17;
+        return st;
+    };
+    const uint64_t thr = (uint64_t)(std::min(p_minor, 0.999999) * 18446744073709551615.0);
+    for (int b = 0; b < blocks; ++b) {
+        uint32_t carry = 0;
+        for (int sp = 0; sp < 255; ++sp) {
+            uint32_t m[4];
+            for (int w = 0; w < 4; ++w) {
+                uint32_t v = 0;
+                for (int i = 0; i < 32; ++i) v |= (uint32_t)(next() < thr) << i;
+                m[w] = v;
+            }
+            tokenize_cells(m, carry, sp > 0, 64, false, h);
+            carry = m[3] >> 30;
+        }
+    }
+    return h;
+}
+
+// One table: codes for cell literals, all match lengths, EOB (+ prefix byte literals when `prefix_hist`).
+inline FusedTable make_table(double p_minor, const uint64_t* prefix_hist /* [256] per-row average x 16, or null */) {
+    const int kBlocks = 4;
+    HistSink h = simulate(p_minor, kBlocks);
+    std::vector<uint64_t> f(286, 0);
+    const uint8_t lit_byte[5] = {'0', '1', '/', '\t', '\n'};
+    const uint64_t scale = 16;  // fixed-point so that per-row prefix averages below one occurrence still count
+    for (int i = 0; i < 5; ++i) f[lit_byte[i]] += (h.nlit[i] * scale) / kBlocks + 1;
+    for (int i = 0; i < 29; ++i) f[257 + i] += (h.nlen[i] * scale) / kBlocks + 1;
+    f[256] = scale;
+    if (prefix_hist)
+        for (int c = 0; c < 256; ++c)
+            if (prefix_hist[c]) f[c] += std::max<uint64_t>(1, prefix_hist[c]);
+    std::vector<uint8_t> ll = huff_lengths(f, 15);
+    std::vector<uint32_t> lc = huff_codes(ll);
+    FusedTable t;
+    memset(&t, 0, sizeof t);
+    for (int len = 3; len <= 258; ++len) {
+        const int ci = len_index(len);
+        const uint32_t c = lc[257 + ci];
+        const uint32_t cl = c >> 24, ex = (uint32_t)kLenExtra[ci];
+        t.len_tok[len] = ((c & 0xFFFFFFu) | ((uint32_t)(len - kLenBase[ci]) << cl)) | ((cl + ex + 1u) << 24);
+    }
+    for (int i = 0; i < 5; ++i) t.lit[i] = lc[lit_byte[i]];
+    t.eob = lc[256];
+    for (int c = 0; c < 256; ++c) t.pre_lit[c] = lc[c];
+    BitString hdr = dynamic_header(ll);
+    t.hdr_bits = hdr.bits;
+    for (size_t i = 0; i < hdr.words.size() && i < 62; ++i) t.hdr[i] = hdr.words[i];
+    if (hdr.words.size() > 62) t.hdr_bits = 0xFFFFFFFFu;  // caller treats as "no table" (cannot happen: < 1 KiB)
+    return t;
+}
+
+}  // namespace hosttab
+}  // namespace dnaf

@@ -276,6 +276,7 @@ __device__ __forceinline__ void span_bounds(uint32_t t, uint32_t len, uint32_t p
 
 // One CTA (256 threads) per BGZF block.
 __global__ void __launch_bounds__(256, 1) k_bgzf_generic(const uint8_t* __restrict__ text, const BlockDesc* __restrict__ blocks,
+                                                        const uint32_t* __restrict__ slot_idx,
                                                         const uint32_t* __restrict__ g_crctab,
                                                         const uint32_t* __restrict__ g_xpow8, uint8_t* __restrict__ slots,
                                                         uint32_t* __restrict__ sizes, uint32_t* __restrict__ crcs) {
@@ -340,7 +341,8 @@ __global__ void __launch_bounds__(256, 1) k_bgzf_generic(const uint8_t* __restri
     const uint32_t payload = (data_bits + 7u) / 8u;
     const bool stored = payload > n + 5u || payload > kSlot - 26u;
 
-    uint8_t* slot = slots + (uint64_t)blockIdx.x * kSlot;
+    const uint32_t slot_no = slot_idx ? slot_idx[blockIdx.x] : blockIdx.x;
+    uint8_t* slot = slots + (uint64_t)slot_no * kSlot;
     uint32_t out_payload;
     if (!stored) {
         // -- pass 3: emit
@@ -370,8 +372,8 @@ __global__ void __launch_bounds__(256, 1) k_bgzf_generic(const uint8_t* __restri
         uint8_t* tail = slot + 18 + out_payload;
         for (int i = 0; i < 4; ++i) tail[i] = (uint8_t)(crc32 >> (8 * i));
         for (int i = 0; i < 4; ++i) tail[4 + i] = (uint8_t)(n >> (8 * i));
-        sizes[blockIdx.x] = out_payload + 26u;
-        crcs[blockIdx.x] = crc32;
+        sizes[slot_no] = out_payload + 26u;
+        crcs[slot_no] = crc32;
     }
 }
 

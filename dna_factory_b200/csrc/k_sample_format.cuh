@@ -28,15 +28,15 @@ struct SnpView {
     const uint64_t* pre_off; // [S+1]
 };
 
-// One thread per (row, group of 32 allele slots).
-__global__ void __launch_bounds__(256) k_sample(SampleView sv, SnpView nv, uint64_t row0, uint64_t row_base, uint32_t n_rows,
-                                               uint32_t k0, uint32_t k1, uint32_t* __restrict__ plane0,
-                                               uint32_t* __restrict__ plane1) {
+// One thread per (row, group of 32 allele slots).  Local row r is global row row0 + (row_idx ? row_idx[r] : r).
+__global__ void __launch_bounds__(256) k_sample(SampleView sv, SnpView nv, uint64_t row0, const uint32_t* __restrict__ row_idx,
+                                               uint64_t row_base, uint32_t n_rows, uint32_t k0, uint32_t k1,
+                                               uint32_t* __restrict__ plane0, uint32_t* __restrict__ plane1) {
     const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (uint64_t)n_rows * sv.groups) return;
     const uint32_t r = (uint32_t)(idx / sv.groups);
     const uint32_t g = (uint32_t)(idx % sv.groups);
-    const uint64_t row = row0 + r;
+    const uint64_t row = row0 + (row_idx ? row_idx[r] : r);
     const uint4 t4 = reinterpret_cast<const uint4*>(nv.thr)[row];
     const uint32_t thr[4] = {t4.x, t4.y, t4.z, t4.w};
     const uint32_t slots = 2u * sv.n - 32u * g;
@@ -49,13 +49,14 @@ __global__ void __launch_bounds__(256) k_sample(SampleView sv, SnpView nv, uint6
 
 // Forced-minor cells: allele index 1 in both slots (the formatter ignores slot 1 of haploid cells and
 // everything on '.' cells, which is the order of the tests at pop_factory.py:481-499).
-__global__ void k_overrides(const uint64_t* __restrict__ orow, const uint32_t* __restrict__ osamp, uint64_t first,
-                            uint64_t count, uint64_t row0, uint32_t groups, uint32_t n_samples,
-                            uint32_t* __restrict__ plane0, uint32_t* __restrict__ plane1) {
+// olocal[t] = local row (index into the plane buffers), osamp[t] = sample.
+__global__ void k_overrides(const uint32_t* __restrict__ olocal, const uint32_t* __restrict__ osamp, uint64_t count,
+                            uint32_t groups, uint32_t n_samples, uint32_t* __restrict__ plane0,
+                            uint32_t* __restrict__ plane1) {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= count) return;
-    const uint64_t r = orow[first + t] - row0;
-    const uint32_t i = osamp[first + t];
+    const uint64_t r = olocal[t];
+    const uint32_t i = osamp[t];
     if (i >= n_samples) return;
     const uint64_t w = r * groups + (i >> 4);
     const uint32_t m = 3u << ((2u * i) & 31u);
@@ -67,16 +68,18 @@ __device__ __forceinline__ uint32_t cell_width(uint8_t cls, bool male) {
     return (cls == kAuto || (cls == kX && !male)) ? 4u : 2u;
 }
 
-// Kernel 2: one CTA per row; threads stride over samples.  Text goes to text[row_off[r] - text0 ...].
-__global__ void __launch_bounds__(256) k_format(SampleView sv, SnpView nv, uint64_t row0, const uint64_t* __restrict__ row_off,
+// Kernel 2: one CTA per row; threads stride over samples.  Row r goes to text + sub_off[r] when a row
+// subset is formatted (row_idx != null), else to text + row_off[row] - text0.
+__global__ void __launch_bounds__(256) k_format(SampleView sv, SnpView nv, uint64_t row0, const uint32_t* __restrict__ row_idx,
+                                               const uint64_t* __restrict__ sub_off, const uint64_t* __restrict__ row_off,
                                                uint64_t text0, const uint32_t* __restrict__ plane0,
                                                const uint32_t* __restrict__ plane1, uint8_t* __restrict__ text) {
     const uint32_t r = blockIdx.x;
-    const uint64_t row = row0 + r;
+    const uint64_t row = row0 + (row_idx ? row_idx[r] : r);
     const uint8_t cls = nv.cls[row];
     const uint64_t pb = nv.pre_off[row];
     const uint32_t plen = (uint32_t)(nv.pre_off[row + 1] - pb);
-    uint8_t* out = text + (row_off[row] - text0);
+    uint8_t* out = text + (row_idx ? sub_off[r] : row_off[row] - text0);
     for (uint32_t i = threadIdx.x; i < plen; i += blockDim.x) out[i] = nv.prefix[pb + i];
     uint8_t* body = out + plen;
     if (sv.n == 0) {

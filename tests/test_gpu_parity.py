@@ -104,6 +104,26 @@ def test_oracle_vs_cuda_synthetic(native, n, s, seed):
     assert sub == want[int(row_off[mid]):]
 
 
+@pytest.mark.parametrize("n,s,seed", [(4096, 12, 31), (4097, 12, 32), (4160, 8, 33), (16256, 5, 34), (16257, 5, 35),
+                                      (16320, 4, 36), (20000, 24, 37), (33000, 6, 38)])
+def test_fused_kernel_vs_oracle_and_generic(native, n, s, seed):
+    """The fused sample+format+deflate kernel (autosome rows of >= 4096 samples) against the oracle text and
+    against the three-kernel path; block streams may differ, decompressed bytes may not."""
+    from oracle import oracle
+    case = synth_case(n, s, seed=seed, chroms=['1', '2', '1', '7', 'X', '22', 'Y'], n_del=40)
+    want, _ = oracle.rows(case.samples, case.snps, case.seed, 0, n_threads=4)
+    eng = _engine(native, case, chunk=8 << 20)
+    fused, st_f = eng.generate(0, s, case.seed, level=2)
+    assert st_f["ms_fused"] > 0
+    assert oracle.bgzf_decompress(fused)[0] == want
+    eng.set_fused(False)
+    plain, st_p = eng.generate(0, s, case.seed, level=2)
+    assert st_p["ms_fused"] == 0
+    assert oracle.bgzf_decompress(plain)[0] == want
+    # the static per-MAF-bucket codes must stay close to the per-block dynamic codes
+    assert st_f["bgzf_bytes"] < 1.10 * st_p["bgzf_bytes"] + 4096
+
+
 def test_bgzf_compress_arbitrary_bytes(native):
     from oracle import oracle
     _native, _ = native
