@@ -136,6 +136,9 @@ struct dnaf_ctx {
     std::vector<uint64_t> goff;
     uint64_t gen_text_bytes = 0;
     uint32_t pass_blocks = 0;
+    uint32_t fused_threads = 256;
+    std::map<std::pair<uint64_t, uint64_t>, FusedTable> table_cache;
+    bool etab_ok = false;
 };
 
 namespace {
@@ -240,24 +243,40 @@ int ensure_fused(dnaf_ctx* c, const uint8_t* kk, const uint32_t* thr, const uint
         const uint32_t t = kk[r] >= 2 ? thr[r * 4] : 0xFFFFFFFFu;
         c->h_bucket[r] = (uint16_t)keys[t >> shift];
     }
-    // prefix byte statistics (per row, x16 fixed point)
+    // prefix byte model (x16 fixed point per row): which bytes occur, weighted by kind -- deliberately not the
+    // exact counts, so that tables can be cached across set_snps calls with similar prefixes
     std::vector<uint64_t> ph(256, 0);
     const uint64_t total = pre_off[c->S];
-    for (uint64_t i = 0; i < total; ++i) ph[prefix[i]]++;
-    for (auto& v : ph)
-        if (v) v = std::max<uint64_t>(1, (v * 16 + c->S / 2) / c->S);
+    for (uint64_t i = 0; i < total; ++i) ph[prefix[i]] = 1;
+    uint64_t ph_hash = 1469598103934665603ull;
+    for (int b = 0; b < 256; ++b) {
+        if (ph[b]) ph[b] = b == '\t' ? 144 : ((b >= '0' && b <= '9') ? 24 : 16);
+        ph_hash = (ph_hash ^ ph[b]) * 1099511628211ull;
+    }
     std::vector<FusedTable> tabs((size_t)nb * 2);
     for (auto& kv : keys) {
         const uint64_t lo = (uint64_t)kv.first << shift;
         const uint64_t hi = std::min<uint64_t>(0xFFFFFFFFull, lo + ((1ull << shift) - 1));
         const double t_mid = 0.5 * ((double)lo + (double)hi);
         const double p_minor = std::min(1.0, std::max(0.0, 1.0 - (t_mid + 1.0) / 4294967296.0));
-        tabs[2 * kv.second] = hosttab::make_table(p_minor, ph.data());      // segments that carry the row prefix
-        tabs[2 * kv.second + 1] = hosttab::make_table(p_minor, nullptr);    // the others
+        uint64_t pbits;
+        memcpy(&pbits, &p_minor, 8);
+        auto cached = [&](uint64_t variant, const uint64_t* hist) -> const FusedTable& {
+            auto key = std::make_pair(pbits, variant);
+            auto it = c->table_cache.find(key);
+            if (it == c->table_cache.end()) it = c->table_cache.emplace(key, hosttab::make_table(p_minor, hist)).first;
+            return it->second;
+        };
+        tabs[2 * kv.second] = cached(ph_hash, ph.data());   // segments that carry the row prefix
+        tabs[2 * kv.second + 1] = cached(0, nullptr);       // the others
         if (tabs[2 * kv.second].hdr_bits == 0xFFFFFFFFu || tabs[2 * kv.second + 1].hdr_bits == 0xFFFFFFFFu) return DNAF_OK;
     }
     int rc = upload(c, c->d_ftables, tabs.data(), tabs.size());
     if (rc) return rc;
+    if (c->etab_ok) {
+        c->fused_ok = true;
+        return DNAF_OK;
+    }
     // E tables: contribution of mask byte b at byte k of word w to the span's linear CRC (span end aligned)
     std::vector<uint32_t> tab(256), xp(257);
     for (uint32_t i = 0; i < 256; ++i) {
@@ -281,14 +300,17 @@ int ensure_fused(dnaf_ctx* c, const uint8_t* kk, const uint32_t* thr, const uint
             }
     rc = upload(c, c->d_etab, etab.data(), etab.size());
     if (rc) return rc;
+    c->etab_ok = true;
     c->fused_ok = true;
     return DNAF_OK;
 }
 
-// Segments of an autosome row and the linear CRC of their all-reference template bodies.
+// Segments of an autosome row (balanced, at most 254 spans of 64 samples each) and the linear CRC of their
+// all-reference template bodies.
 void build_segments(dnaf_ctx* c) {
     c->h_seg_cell0.clear();
     c->h_seg_crc.clear();
+    c->fused_threads = 64;
     if (c->n == 0) return;
     std::vector<uint32_t> tab(256);
     for (uint32_t i = 0; i < 256; ++i) {
@@ -299,21 +321,22 @@ void build_segments(dnaf_ctx* c) {
     std::vector<uint8_t> body((size_t)4 * c->n);
     for (uint32_t i = 0; i < c->n; ++i) memcpy(&body[4ull * i], "0/0\t", 4);
     body.back() = '\n';
-    uint32_t cell = 0;
-    bool first = true;
-    while (cell < c->n) {
-        const uint32_t cap = (first ? 254u : 255u) * 64u;
-        const uint32_t cnt = std::min(cap, c->n - cell);
+    const uint32_t spans = (c->n + 63u) / 64u;
+    const uint32_t nseg = (spans + 253u) / 254u;
+    const uint32_t per = (spans + nseg - 1u) / nseg;  // spans per segment: <= 254, so prefix + body <= kBlk
+    for (uint32_t sg = 0; sg < nseg; ++sg) {
+        const uint32_t cell = std::min(c->n, sg * per * 64u);
+        const uint32_t cnt = std::min(c->n, (sg + 1) * per * 64u) - cell;
+        if (!cnt) break;
         c->h_seg_cell0.push_back(cell);
         c->h_seg_crc.push_back(raw_crc(&body[4ull * cell], 4ull * cnt, tab.data()));
-        cell += cnt;
-        first = false;
     }
     c->h_seg_cell0.push_back(c->n);
+    c->fused_threads = std::max(64u, (per + 31u) / 32u * 32u);
 }
 
 inline bool row_is_fused(const dnaf_ctx* c, uint64_t r, const uint8_t* hk) {
-    return c->fused && c->fused_ok && c->h_cls[r] == kAuto && hk[r] <= 2 && c->h_plen[r] >= 1 && c->h_plen[r] <= 256 &&
+    return c->fused && c->fused_ok && c->h_cls[r] == kAuto && hk[r] <= 2 && c->h_plen[r] >= 1 && c->h_plen[r] <= 64 &&
            4ull * c->n >= kFusedMinRowBytes;
 }
 
@@ -610,7 +633,7 @@ int generate_impl(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t se
             fa.slots = c->d_slots.as<uint8_t>();
             fa.sizes = c->d_sizes.as<uint32_t>();
             fa.crcs = c->d_crcs.as<uint32_t>();
-            k_fused_auto<<<(uint32_t)c->fplan.size(), kFusedThreads, 0, c->stream>>>(fa);
+            k_fused_auto<<<(uint32_t)c->fplan.size(), c->fused_threads, 0, c->stream>>>(fa);
             local.kernel_launches += 1;
             CU(c, cudaGetLastError());
         }

@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(256, 1) k_bgzf_generic(const uint8_t* __restri
     const bool stored = payload > n + 5u || payload > kSlot - 26u;
 
     const uint32_t slot_no = slot_idx ? slot_idx[blockIdx.x] : blockIdx.x;
-    uint8_t* slot = slots + (uint64_t)slot_no * kSlot;
+    uint8_t* slot = slots + (uint64_t)slot_no * kSlot + 2;  // blocks start at slot + 2 (see k_fused.cuh)
     uint32_t out_payload;
     if (!stored) {
         // -- pass 3: emit
@@ -413,27 +413,31 @@ __global__ void __launch_bounds__(1024) k_scan_sizes(const uint32_t* __restrict_
 __global__ void __launch_bounds__(256) k_compact(const uint8_t* __restrict__ slots, uint32_t slot_stride,
                                                 const uint32_t* __restrict__ sizes, const uint64_t* __restrict__ offsets,
                                                 uint8_t* __restrict__ out) {
-    const uint8_t* src = slots + (uint64_t)blockIdx.x * slot_stride;
+    const uint8_t* src = slots + (uint64_t)blockIdx.x * slot_stride + 2;
     uint8_t* dst = out + offsets[blockIdx.x];
     const uint32_t n = sizes[blockIdx.x];
-    // destination alignment decides the vector width; source slots are 16-byte aligned
+    // 16-byte stores to the destination; the source (slot + 2) is read as 16-bit units
     const uint32_t head = min(n, (uint32_t)((16u - (reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u));
     for (uint32_t i = threadIdx.x; i < head; i += blockDim.x) dst[i] = src[i];
     const uint32_t body = (n - head) / 16u;
     uint4* d16 = reinterpret_cast<uint4*>(dst + head);
     for (uint32_t i = threadIdx.x; i < body; i += blockDim.x) {
         const uint8_t* p = src + head + 16u * i;
-        uint4 v;
-        if ((head & 3u) == 0) {
+        uint32_t w[4];
+        if ((reinterpret_cast<uintptr_t>(p) & 3u) == 0) {
             const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
-            v = make_uint4(q[0], q[1], q[2], q[3]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) w[k] = q[k];
+        } else if ((reinterpret_cast<uintptr_t>(p) & 1u) == 0) {
+            const uint16_t* q = reinterpret_cast<const uint16_t*>(p);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) w[k] = q[2 * k] | ((uint32_t)q[2 * k + 1] << 16);
         } else {
-            uint32_t w[4];
+#pragma unroll
             for (int k = 0; k < 4; ++k)
                 w[k] = p[4 * k] | (p[4 * k + 1] << 8) | (p[4 * k + 2] << 16) | ((uint32_t)p[4 * k + 3] << 24);
-            v = make_uint4(w[0], w[1], w[2], w[3]);
         }
-        d16[i] = v;
+        d16[i] = make_uint4(w[0], w[1], w[2], w[3]);
     }
     for (uint32_t i = head + body * 16u + threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
 }

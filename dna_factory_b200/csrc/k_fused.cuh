@@ -20,8 +20,6 @@
 
 namespace dnaf {
 
-constexpr int kFusedThreads = 256;
-constexpr uint32_t kFusedOutWords = 5120;  // 20 KiB of payload staged in shared memory; larger -> global path
 
 // literal symbol ids of the five bytes a genotype cell can hold
 enum : int { kLit0 = 0, kLit1 = 1, kLitSlash = 2, kLitTab = 3, kLitNl = 4 };
@@ -53,17 +51,25 @@ __host__ __device__ __forceinline__ uint32_t pick4(const uint32_t m[4], int w) {
 
 // ---- mask-domain P4 tokeniser, shared by the kernel and by the host's table builder ----
 // m[0..3]: minor-allele bits of the span's 128 allele slots; carry: the two bits of the previous cell.
+// One loop over all 128 mismatch bits (not one per word) keeps a warp's trip count at the maximum of the
+// per-thread totals instead of the sum of per-word maxima.
 template <class Sink>
 __host__ __device__ __forceinline__ void tokenize_cells(const uint32_t m[4], uint32_t carry, bool has_prev, int ncells,
                                                         bool ends_row, Sink& sink) {
     const int span_len = 4 * ncells;
     const int end = ends_row ? span_len - 1 : span_len;  // the final '\n' is always a literal
     int prev_end = 0;
-    uint32_t x[4];
-    x[0] = m[0] ^ ((m[0] << 2) | (carry & 3u));
-    x[1] = m[1] ^ ((m[1] << 2) | (m[0] >> 30));
-    x[2] = m[2] ^ ((m[2] << 2) | (m[1] >> 30));
-    x[3] = m[3] ^ ((m[3] << 2) | (m[2] >> 30));
+    uint32_t x0 = m[0] ^ ((m[0] << 2) | (carry & 3u));
+    uint32_t x1 = m[1] ^ ((m[1] << 2) | (m[0] >> 30));
+    uint32_t x2 = m[2] ^ ((m[2] << 2) | (m[1] >> 30));
+    uint32_t x3 = m[3] ^ ((m[3] << 2) | (m[2] >> 30));
+    {   // only the first 2*ncells allele slots exist
+        const int na = 2 * ncells;
+        if (na < 128) x3 = na > 96 ? (x3 & (0xFFFFFFFFu >> (128 - na))) : 0u;
+        if (na < 96) x2 = na > 64 ? (x2 & (0xFFFFFFFFu >> (96 - na))) : 0u;
+        if (na < 64) x1 = na > 32 ? (x1 & (0xFFFFFFFFu >> (64 - na))) : 0u;
+        if (na < 32) x0 &= 0xFFFFFFFFu >> (32 - na);
+    }
     if (!has_prev) {  // nothing 4 bytes back that is a cell: the first cell goes out as literals
         sink.lit((int)(m[0] & 1u));
         sink.lit(kLitSlash);
@@ -74,7 +80,7 @@ __host__ __device__ __forceinline__ void tokenize_cells(const uint32_t m[4], uin
         }
         sink.lit(kLitTab);
         prev_end = 4;
-        x[0] &= ~3u;
+        x0 &= ~3u;
     }
     auto gap_to = [&](int p) {  // bytes [prev_end, p) are predicted
         const int gap = p - prev_end;
@@ -87,22 +93,25 @@ __host__ __device__ __forceinline__ void tokenize_cells(const uint32_t m[4], uin
             }
         }
     };
-#pragma unroll
-    for (int w = 0; w < 4; ++w) {
-        uint32_t xw = x[w];
-        if (32 * w + 32 > 2 * ncells) xw &= (2 * ncells > 32 * w) ? (0xFFFFFFFFu >> (32 * w + 32 - 2 * ncells)) : 0u;
-        while (xw) {
+    for (;;) {
+        int w;
+        uint32_t xw;
+        if (x0) { w = 0; xw = x0; }
+        else if (x1) { w = 1; xw = x1; }
+        else if (x2) { w = 2; xw = x2; }
+        else if (x3) { w = 3; xw = x3; }
+        else break;
 #ifdef __CUDA_ARCH__
-            const int b = __ffs((int)xw) - 1;
+        const int b = __ffs((int)xw) - 1;
 #else
-            const int b = __builtin_ctz(xw);
+        const int b = __builtin_ctz(xw);
 #endif
-            xw &= xw - 1;
-            const int p = 2 * (32 * w + b);
-            gap_to(p);
-            sink.lit((int)((m[w] >> b) & 1u));
-            prev_end = p + 1;
-        }
+        xw &= xw - 1;
+        if (w == 0) x0 = xw; else if (w == 1) x1 = xw; else if (w == 2) x2 = xw; else x3 = xw;
+        const int p = 2 * (32 * w + b);
+        gap_to(p);
+        sink.lit((int)((pick4(m, w) >> b) & 1u));
+        prev_end = p + 1;
     }
     gap_to(end);
     if (ends_row) sink.lit(kLitNl);
@@ -116,51 +125,61 @@ struct FusedCount {
     __host__ __device__ void match(int len) { bits += len_tok[len] >> 24; }
 };
 
-// Appends bits at an arbitrary bit offset; the first and the last word it touches are shared with the
-// neighbouring threads (atomic OR into zeroed memory), the words in between are owned.
-template <bool kGlobal>
-struct FusedEmit {
+constexpr int kStageWords = 16;  // per-thread staging capacity (512 bits); beyond it the block re-emits
+
+// Pass-1 sink: appends this thread's bits to its private staging words stage[wi * stride] (word-interleaved
+// across threads, so a warp writing word wi hits 32 different banks).  Keeps counting past the capacity.
+struct FusedStage {
     const uint32_t* len_tok;
     const uint32_t* lit_tok;
-    uint32_t* words;
-    uint32_t wi;
-    uint32_t nacc;
+    uint32_t* stage;   // already offset by the thread id
+    uint32_t stride;
+    uint32_t wi, nacc, bits;
     uint64_t acc;
-    bool first;
-    __device__ void init(uint32_t* w, uint32_t bitpos) {
-        words = w;
-        wi = bitpos >> 5;
-        nacc = bitpos & 31u;
-        acc = 0;
-        first = true;
-    }
     __device__ void put(uint32_t v, uint32_t n) {
         acc |= (uint64_t)v << nacc;
         nacc += n;
+        bits += n;
         if (nacc >= 32) {
-            if (first || kGlobal) atomicOr(&words[wi], (uint32_t)acc);
-            else words[wi] = (uint32_t)acc;
-            first = false;
+            if (wi < (uint32_t)kStageWords) stage[wi * stride] = (uint32_t)acc;
             ++wi;
             acc >>= 32;
             nacc -= 32;
         }
     }
     __device__ void finish() {
-        if (nacc) atomicOr(&words[wi], (uint32_t)acc);
+        if (nacc && wi < (uint32_t)kStageWords) stage[wi * stride] = (uint32_t)acc;
     }
     __device__ void lit(int id) { put(lit_tok[id] & 0xFFFFFFu, lit_tok[id] >> 24); }
     __device__ void match(int len) { put(len_tok[len] & 0xFFFFFFu, len_tok[len] >> 24); }
 };
 
+// Slow-path sink (a thread overflowed its staging): ORs every token straight into the zeroed output words.
+struct FusedEmit {
+    const uint32_t* len_tok;
+    const uint32_t* lit_tok;
+    uint32_t* words;
+    uint32_t pos;
+    __device__ void put(uint32_t v, uint32_t n) {
+        const uint32_t wi = pos >> 5, sh = pos & 31u;
+        atomicOr(&words[wi], v << sh);
+        if (sh + n > 32) atomicOr(&words[wi + 1], v >> (32 - sh));
+        pos += n;
+    }
+    __device__ void lit(int id) { put(lit_tok[id] & 0xFFFFFFu, lit_tok[id] >> 24); }
+    __device__ void match(int len) { put(len_tok[len] & 0xFFFFFFu, len_tok[len] >> 24); }
+};
+
+constexpr int kFusedMaxThreads = 256;
+
 struct FusedSmem {
-    uint32_t out[kFusedOutWords];
+    uint32_t stage[kStageWords * kFusedMaxThreads];
     uint32_t len_tok[260];
     uint32_t lit_tok[8];
-    uint32_t last_bits[kFusedThreads];
-    uint32_t warp_tmp[8];
+    uint32_t last_bits[kFusedMaxThreads];
+    uint32_t warp_pre[8], warp_span[8];
     uint32_t crc_acc;
-    uint32_t total_bits;
+    uint32_t overflow;
 };
 
 struct FusedArgs {
@@ -180,9 +199,13 @@ struct FusedArgs {
     uint32_t* crcs;
 };
 
-__global__ void __launch_bounds__(kFusedThreads, 4) k_fused_auto(const FusedArgs a) {
+// Slot layout: the BGZF block starts at slot + 2, so that its deflate payload (slot + 20) is word aligned.
+constexpr uint32_t kSlotLead = 2;
+
+// One CTA per BGZF block; thread t owns span t (64 samples) and, when t < prefix length, prefix byte t.
+__global__ void __launch_bounds__(kFusedMaxThreads, 4) k_fused_auto(const FusedArgs a) {
     __shared__ FusedSmem s;
-    const uint32_t tid = threadIdx.x;
+    const uint32_t tid = threadIdx.x, nthr = blockDim.x;
     const FusedDesc d = a.desc[blockIdx.x];
     const FusedTable* __restrict__ tb = a.tables + d.table;
     const bool has_prefix = d.flags & 1u, ends_row = (d.flags >> 1) & 1u;
@@ -190,15 +213,14 @@ __global__ void __launch_bounds__(kFusedThreads, 4) k_fused_auto(const FusedArgs
     const uint32_t plen = has_prefix ? (uint32_t)(a.nv.pre_off[d.row + 1] - pb) : 0u;
     const uint32_t n = plen + 4u * d.ncells;  // text bytes of this block
 
-    for (uint32_t i = tid; i < 260; i += kFusedThreads) s.len_tok[i] = tb->len_tok[i];
+    for (uint32_t i = tid; i < 260; i += nthr) s.len_tok[i] = tb->len_tok[i];
     if (tid < 8) s.lit_tok[tid] = tb->lit[tid];
-    if (tid == 0) s.crc_acc = 0;
+    if (tid == 0) { s.crc_acc = 0; s.overflow = 0; }
 
     // ---- draw this span's 128 allele bits
-    const int span = (int)tid - 1;  // thread 0 owns the prefix
-    const uint32_t cs = d.cell0 + 64u * (uint32_t)(span < 0 ? 0 : span);
+    const uint32_t cs = d.cell0 + 64u * tid;
     int nc = 0;
-    if (span >= 0 && 64u * (uint32_t)span < d.ncells) nc = (int)min(64u, d.ncells - 64u * (uint32_t)span);
+    if (64u * tid < d.ncells) nc = (int)min(64u, d.ncells - 64u * tid);
     uint32_t m[4] = {0, 0, 0, 0};
     if (nc > 0 && a.nv.k[d.row] == 2) {
         const uint32_t thr = a.nv.thr[d.row * 4];
@@ -230,51 +252,62 @@ __global__ void __launch_bounds__(kFusedThreads, 4) k_fused_auto(const FusedArgs
     s.last_bits[tid] = m[3] >> 30;
     __syncthreads();
     const uint32_t carry = tid ? s.last_bits[tid - 1] : 0u;
-    const bool has_prev = span > 0;
-    const bool my_end = ends_row && nc > 0 && 64u * (uint32_t)span + (uint32_t)nc == d.ncells;
+    const bool has_prev = tid > 0;
+    const bool my_end = ends_row && nc > 0 && 64u * tid + (uint32_t)nc == d.ncells;
+    const bool last_span = nc > 0 && 64u * tid + (uint32_t)nc == d.ncells;
+    const uint32_t eob = tb->eob;
 
-    // ---- pass 1: bits this thread will emit
-    FusedCount cnt{s.len_tok, s.lit_tok, 0};
-    uint32_t pre_crc = 0;
-    if (tid == 0) {
-        for (uint32_t i = 0; i < plen; ++i) {
-            const uint8_t c = a.nv.prefix[pb + i];
-            cnt.bits += tb->pre_lit[c] >> 24;
-            pre_crc = a.crctab[(pre_crc ^ c) & 0xFFu] ^ (pre_crc >> 8);
-        }
-    } else if (nc > 0) {
-        tokenize_cells(m, carry, has_prev, nc, my_end, cnt);
+    // ---- pass 1: tokens of this span, staged privately
+    FusedStage st{s.len_tok, s.lit_tok, s.stage + tid, nthr, 0, 0, 0, 0};
+    if (nc > 0) {
+        tokenize_cells(m, carry, has_prev, nc, my_end, st);
+        if (last_span) st.put(eob & 0xFFFFFFu, eob >> 24);
+        st.finish();
+        if (st.bits > 32u * kStageWords) s.overflow = 1;
     }
-    {   // exclusive scan over the CTA
-        uint32_t v = cnt.bits;
+    // prefix byte of this thread: literal code, and its share of the CRC
+    uint32_t pre_tok = 0;
+    uint32_t crc = 0;
+    if (tid < plen) {
+        const uint8_t c = a.nv.prefix[pb + tid];
+        pre_tok = tb->pre_lit[c];
+        crc = gf2_mulmod(a.xpow8[n - 1u - tid], __ldg(&a.crctab[c]));
+    }
+    const uint32_t pre_bits = pre_tok >> 24;
+    // ---- exclusive scans over the CTA: prefix literal bits and span bits
+    uint32_t pre_off, span_off, total_pre, total_span;
+    {
+        uint32_t v0 = pre_bits, v1 = st.bits;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, v, o);
-            if ((tid & 31u) >= (uint32_t)o) v += u;
+            const uint32_t u0 = __shfl_up_sync(0xFFFFFFFFu, v0, o);
+            const uint32_t u1 = __shfl_up_sync(0xFFFFFFFFu, v1, o);
+            if ((tid & 31u) >= (uint32_t)o) { v0 += u0; v1 += u1; }
         }
-        if ((tid & 31u) == 31u) s.warp_tmp[tid >> 5] = v;
+        if ((tid & 31u) == 31u) { s.warp_pre[tid >> 5] = v0; s.warp_span[tid >> 5] = v1; }
         __syncthreads();
-        uint32_t base = tb->hdr_bits;
-        for (uint32_t wv = 0; wv < (tid >> 5); ++wv) base += s.warp_tmp[wv];
-        cnt.bits = base + v - cnt.bits;  // now: this thread's first bit
-        if (tid == kFusedThreads - 1) s.total_bits = base + v;
+        uint32_t b0 = 0, b1 = 0, t0 = 0, t1 = 0;
+        const uint32_t nw = nthr >> 5;
+        for (uint32_t wv = 0; wv < nw; ++wv) {
+            if (wv < (tid >> 5)) { b0 += s.warp_pre[wv]; b1 += s.warp_span[wv]; }
+            t0 += s.warp_pre[wv];
+            t1 += s.warp_span[wv];
+        }
+        pre_off = b0 + v0 - pre_bits;
+        span_off = b1 + v1 - st.bits;
+        total_pre = t0;
+        total_span = t1;
     }
-    __syncthreads();
-    const uint32_t eob = tb->eob;
-    const uint32_t data_bits = s.total_bits + (eob >> 24);
+    const uint32_t hdr_bits = tb->hdr_bits;
+    const uint32_t data_bits = hdr_bits + total_pre + total_span;
     const uint32_t payload = (data_bits + 7u) / 8u;
     const uint32_t out_words = (data_bits + 31u) / 32u;
     const bool stored = payload > n + 5u;  // cannot happen with sane tables; keeps BSIZE <= 64 KiB regardless
-    const bool in_smem = out_words <= kFusedOutWords;
-    uint8_t* slot = a.slots + (uint64_t)d.slot * kSlot;
-    uint32_t* gwords = reinterpret_cast<uint32_t*>(slot + 20);  // 4-byte aligned staging inside the slot
+    uint8_t* blk = a.slots + (uint64_t)d.slot * kSlot + kSlotLead;
+    uint32_t* words = reinterpret_cast<uint32_t*>(blk + 18);  // 4-byte aligned
 
-    // ---- CRC32: template ^ delta (affine), every thread shifts its span's share to the block end
-    uint32_t crc = 0;
-    if (tid == 0) {
-        crc = d.body_crc ^ gf2_mulmod(a.xpow8[n], 0xFFFFFFFFu);
-        if (pre_crc) crc ^= gf2_mulmod(a.xpow8[n - plen], pre_crc);
-    } else if (nc > 0 && (m[0] | m[1] | m[2] | m[3])) {
+    // ---- CRC32: template ^ delta (affine); every thread shifts its share to the block end
+    if (nc > 0 && (m[0] | m[1] | m[2] | m[3])) {
         uint32_t mm[4] = {m[0], m[1], m[2], m[3]};
         if (nc < 64) {  // partial last span: align its end with the table's span end (128-bit left shift)
             const uint32_t sh = 2u * (64u - (uint32_t)nc);
@@ -292,77 +325,62 @@ __global__ void __launch_bounds__(kFusedThreads, 4) k_fused_auto(const FusedArgs
         for (int w = 0; w < 4; ++w)
 #pragma unroll
             for (int k = 0; k < 4; ++k) sp ^= __ldg(&a.etab[(4 * w + k) * 256 + ((mm[w] >> (8 * k)) & 0xFFu)]);
-        const uint32_t span_end = plen + 4u * (64u * (uint32_t)span + (uint32_t)nc);
-        crc = gf2_mulmod(a.xpow8[n - span_end], sp);
+        const uint32_t span_end = plen + 4u * (64u * tid + (uint32_t)nc);
+        crc ^= gf2_mulmod(a.xpow8[n - span_end], sp);
     }
+    if (tid == 0) crc ^= d.body_crc ^ gf2_mulmod(a.xpow8[n], 0xFFFFFFFFu);
     crc = warp_xor(crc);
     if ((tid & 31u) == 0 && crc) atomicXor(&s.crc_acc, crc);
 
     uint32_t out_payload;
     if (!stored) {
-        uint32_t* words = in_smem ? s.out : gwords;
-        for (uint32_t i = tid; i < out_words + 1; i += kFusedThreads) words[i] = i < (tb->hdr_bits + 31u) / 32u ? tb->hdr[i] : 0u;
-        if (!in_smem) __threadfence();
+        // zero the words that will be OR-ed into (header words are written, not OR-ed)
+        const uint32_t hdr_words = (hdr_bits + 31u) / 32u;
+        for (uint32_t i = tid; i < out_words + 1u; i += nthr) words[i] = i < hdr_words ? tb->hdr[i] : 0u;
         __syncthreads();
-        // ---- pass 2: emit
-        if (in_smem) {
-            FusedEmit<false> em{s.len_tok, s.lit_tok};
-            em.init(words, cnt.bits);
-            if (tid == 0) {
-                for (uint32_t i = 0; i < plen; ++i) {
-                    const uint32_t c = tb->pre_lit[a.nv.prefix[pb + i]];
-                    em.put(c & 0xFFFFFFu, c >> 24);
-                }
-            } else if (nc > 0) {
-                tokenize_cells(m, carry, has_prev, nc, my_end, em);
-            }
-            if (tid == kFusedThreads - 1) em.put(eob & 0xFFFFFFu, eob >> 24);
-            em.finish();
-        } else {
-            FusedEmit<true> em{s.len_tok, s.lit_tok};
-            em.init(words, cnt.bits);
-            if (tid == 0) {
-                for (uint32_t i = 0; i < plen; ++i) {
-                    const uint32_t c = tb->pre_lit[a.nv.prefix[pb + i]];
-                    em.put(c & 0xFFFFFFu, c >> 24);
-                }
-            } else if (nc > 0) {
-                tokenize_cells(m, carry, has_prev, nc, my_end, em);
-            }
-            if (tid == kFusedThreads - 1) em.put(eob & 0xFFFFFFu, eob >> 24);
-            em.finish();
-            __threadfence();
+        const bool overflow = s.overflow != 0;
+        if (pre_bits) {  // prefix literal: at most 15 bits
+            const uint32_t pos = hdr_bits + pre_off, wi = pos >> 5, sh = pos & 31u, v = pre_tok & 0xFFFFFFu;
+            atomicOr(&words[wi], v << sh);
+            if (sh + pre_bits > 32) atomicOr(&words[wi + 1], v >> (32 - sh));
         }
-        __syncthreads();
-        // payload goes to slot + 18; staged words sit at slot + 20 (global path) or in shared memory
-        if (in_smem) {
-            const uint8_t* ob = reinterpret_cast<const uint8_t*>(s.out);
-            // slot + 18 is 2-byte aligned: move 16-bit units
-            const uint16_t* o16 = reinterpret_cast<const uint16_t*>(ob);
-            uint16_t* d16 = reinterpret_cast<uint16_t*>(slot + 18);
-            for (uint32_t i = tid; i < (payload + 1u) / 2u; i += kFusedThreads) d16[i] = o16[i];
+        const uint32_t dst = hdr_bits + total_pre + span_off;  // first bit of this span in the block
+        if (!overflow) {
+            // ---- pass 2 (fast): move the staged bits to their final position
+            const uint32_t nb = st.bits;
+            if (nb) {
+                const uint32_t sh = dst & 31u;
+                const uint32_t nsrc = (nb + 31u) / 32u;
+                const uint32_t ndst = (sh + nb + 31u) / 32u;
+                uint32_t* o = words + (dst >> 5);
+                uint32_t prev = 0;
+                for (uint32_t k = 0; k < ndst; ++k) {
+                    const uint32_t cur = k < nsrc ? s.stage[k * nthr + tid] : 0u;
+                    const uint32_t v = __funnelshift_l(prev, cur, sh);  // (cur:prev) << sh, upper word
+                    if (k == 0 || k == ndst - 1) atomicOr(&o[k], v);
+                    else o[k] = v;
+                    prev = cur;
+                }
+            }
         } else {
-            // shift down by two bytes in place, front to back, one CTA-wide stripe at a time
-            uint16_t* p16 = reinterpret_cast<uint16_t*>(slot + 18);
-            for (uint32_t base = 0; base < (payload + 1u) / 2u; base += kFusedThreads) {
-                const uint32_t i = base + tid;
-                uint16_t v = 0;
-                if (i < (payload + 1u) / 2u) v = p16[i + 1];
-                __syncthreads();
-                if (i < (payload + 1u) / 2u) p16[i] = v;
-                __syncthreads();
+            // ---- pass 2 (slow): re-tokenise straight into the output words
+            FusedEmit em{s.len_tok, s.lit_tok, words, dst};
+            if (nc > 0) {
+                tokenize_cells(m, carry, has_prev, nc, my_end, em);
+                if (last_span) em.put(eob & 0xFFFFFFu, eob >> 24);
             }
         }
         out_payload = payload;
     } else {
         // stored deflate block: format the text itself (rare safety net)
         if (tid == 0) {
-            slot[18] = 1;
-            slot[19] = (uint8_t)n; slot[20] = (uint8_t)(n >> 8);
-            slot[21] = (uint8_t)~n; slot[22] = (uint8_t)((~n) >> 8);
-            for (uint32_t i = 0; i < plen; ++i) slot[23 + i] = a.nv.prefix[pb + i];
-        } else if (nc > 0) {
-            uint8_t* p = slot + 23 + plen + 256u * (uint32_t)span;
+            blk[18] = 1;
+            blk[19] = (uint8_t)n; blk[20] = (uint8_t)(n >> 8);
+            blk[21] = (uint8_t)~n; blk[22] = (uint8_t)((~n) >> 8);
+        }
+        if (tid < plen) blk[23 + tid] = a.nv.prefix[pb + tid];
+        if (nc > 0) {
+            uint8_t* p = blk + 23 + plen + 256u * tid;
             for (int c = 0; c < nc; ++c) {
                 const uint32_t bits = (pick4(m, c >> 4) >> (2 * (c & 15))) & 3u;
                 p[4 * c] = '0' + (bits & 1u);
@@ -374,17 +392,25 @@ __global__ void __launch_bounds__(kFusedThreads, 4) k_fused_auto(const FusedArgs
         out_payload = n + 5u;
     }
     __syncthreads();
-    if (tid == 0) {
+    if (tid < 26) {  // 18-byte BGZF header, CRC32, ISIZE
         const uint32_t crc32 = ~s.crc_acc;
         const uint32_t bsize = out_payload + 25u;
-        const uint8_t head[18] = {0x1f, 0x8b, 0x08, 0x04, 0, 0, 0, 0, 0, 0xff, 0x06, 0x00, 0x42, 0x43, 0x02, 0x00,
-                                  (uint8_t)bsize, (uint8_t)(bsize >> 8)};
-        for (int i = 0; i < 18; ++i) slot[i] = head[i];
-        uint8_t* tail = slot + 18 + out_payload;
-        for (int i = 0; i < 4; ++i) tail[i] = (uint8_t)(crc32 >> (8 * i));
-        for (int i = 0; i < 4; ++i) tail[4 + i] = (uint8_t)(n >> (8 * i));
-        a.sizes[d.slot] = out_payload + 26u;
-        a.crcs[d.slot] = crc32;
+        uint8_t v;
+        if (tid < 16) {
+            const uint8_t head[16] = {0x1f, 0x8b, 0x08, 0x04, 0, 0, 0, 0, 0, 0xff, 0x06, 0x00, 0x42, 0x43, 0x02, 0x00};
+            v = head[tid];
+            blk[tid] = v;
+        } else if (tid < 18) {
+            blk[tid] = (uint8_t)(bsize >> (8 * (tid - 16)));
+        } else if (tid < 22) {
+            blk[18 + out_payload + (tid - 18)] = (uint8_t)(crc32 >> (8 * (tid - 18)));
+        } else {
+            blk[18 + out_payload + (tid - 18)] = (uint8_t)(n >> (8 * (tid - 22)));
+        }
+        if (tid == 0) {
+            a.sizes[d.slot] = out_payload + 26u;
+            a.crcs[d.slot] = crc32;
+        }
     }
 }
 
