@@ -41,7 +41,7 @@ WORKLOAD = ("C2 pop_factory -s 10000 -c 10000 -x 5000000 -f 0.01 -z 2: one step 
             "x 20000 samples (sample -> VCF GT text -> BGZF)" % ROWS_PER_STEP)
 
 
-def synth_population(n_rows, rank=0):
+def synth_population(n_rows, rank=0, window=ROWS_PER_STEP):
     """Sex vector, control flags and `n_rows` sorted SNP rows shaped like the reference's own generator."""
     from dna_factory_b200 import snp
     rs_state = np.random.get_state()
@@ -49,7 +49,15 @@ def synth_population(n_rows, rank=0):
     n = N_CASES + N_CONTROLS
     sex = np.where(np.random.rand(n) <= MALE_ODDS, 1, 2).astype(np.uint8)       # pop_factory.py:352,365
     ctl = (np.arange(n) < N_CONTROLS).astype(np.uint8)                          # pop_factory.py:358
-    table = snp.SnpFactory.init_from_cdf_file().random_snp_table(n_rows, min_maf=MIN_MAF, vector_alt=True).sorted()
+    # every step's row window is its own sorted draw from the genome-wide distribution, so each step sees the
+    # whole-job chromosome mix (about 4.8 % X and 0.25 % Y rows) instead of ROWS_PER_STEP rows of chromosome 1
+    fac = snp.SnpFactory.init_from_cdf_file()
+    wins = []
+    for w0 in range(0, n_rows, window):
+        t = fac.random_snp_table(min(window, n_rows - w0), min_maf=MIN_MAF, vector_alt=True).sorted()
+        t.ids = t.ids + w0
+        wins.append(t)
+    table = snp.SnpTable.concat(wins)
     # polygenic overrides: ~6 deleterious SNPs per case, as deleterious.yml's groups produce
     n_over = 6 * N_CASES * n_rows // TOTAL_SNPS + 8
     orow = np.sort(np.random.randint(0, n_rows, n_over)).astype(np.uint64)
@@ -104,7 +112,7 @@ def cpu_reference_run(steps, warmup, budget_s=20.0):
     oracle.build()
     cores = oracle.lib().dnaf_or_num_threads()
     rows = 64
-    sex, ctl, table, orow, osamp = synth_population(rows * (steps + warmup))
+    sex, ctl, table, orow, osamp = synth_population(rows * (steps + warmup), window=rows)
     snps_all = table.to_snps()
     from types import SimpleNamespace
     fam = [SimpleNamespace(sex=int(s), is_control=bool(c), deleterious_snps=None if c else {}, person_id=i) for i, (s, c) in
@@ -179,7 +187,7 @@ def main():
     n_steps_total = warmup + args.steps
     # this rank's contiguous SNP range of the population: rows for the device-resident pass, then for e2e
     rows_needed = 2 * n_steps_total * R
-    sex, ctl, table, orow, osamp = synth_population(rows_needed, rank)
+    sex, ctl, table, orow, osamp = synth_population(rows_needed, rank, window=R)
     arrays = table.device_arrays()
     n = len(sex)
     row_base = rank * (TOTAL_SNPS // max(world, 1))

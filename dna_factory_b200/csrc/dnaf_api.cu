@@ -19,6 +19,7 @@
 #include "fused_host.h"
 #include "k_deflate.cuh"
 #include "k_fused.cuh"
+#include "k_fused_text.cuh"
 #include "k_sample_format.cuh"
 #include <map>
 
@@ -87,7 +88,7 @@ struct dnaf_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     std::string err;
-    uint64_t chunk_bytes = 256ull << 20;
+    uint64_t chunk_bytes = 1024ull << 20;
     int fused = 1;
     uint64_t row_base = 0;
 
@@ -123,6 +124,8 @@ struct dnaf_ctx {
     std::vector<BlockDesc> plan;
 
     cudaEvent_t ev[8] = {};
+    cudaStream_t side = nullptr;           // k_fused_text runs here, concurrently with k_fused_auto
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool attr_done = false;
 
     // fused path (k_fused.cuh): per-bucket static codes, CRC helper tables, per-segment template CRCs
@@ -139,6 +142,17 @@ struct dnaf_ctx {
     uint32_t fused_threads = 256;
     std::map<std::pair<uint64_t, uint64_t>, FusedTable> table_cache;
     bool etab_ok = false;
+    std::vector<double> bucket_p;          // minor-allele probability per bucket
+    std::vector<uint64_t> ph;              // prefix byte model
+    uint64_t ph_hash = 0;
+    uint64_t samples_epoch = 0;
+    std::vector<uint64_t> tables_sig;      // what d_ftables currently holds
+    std::vector<uint8_t> h_sex;
+    DevBuf d_crc4, d_xspan, d_tdesc;
+    std::vector<TextDesc> tplan;
+    std::vector<uint32_t> seg_byte0[4];    // k_fused_text segments per chromosome class (+ end sentinel)
+    uint32_t text_threads = 64;
+    bool text_attr_done = false;
 };
 
 namespace {
@@ -191,6 +205,7 @@ SnpView snp_view(const dnaf_ctx* c) {
 }
 
 void build_segments(dnaf_ctx* c);
+int ensure_tables(dnaf_ctx* c);
 
 // Text offset of every row (prefix + class body), host and device copies.
 int ensure_layout(dnaf_ctx* c) {
@@ -206,6 +221,8 @@ int ensure_layout(dnaf_ctx* c) {
     int rc = upload(c, c->d_row_off, c->h_row_off.data(), c->S + 1);
     if (rc) return rc;
     build_segments(c);
+    rc = ensure_tables(c);
+    if (rc) return rc;
     c->layout_ok = true;
     return DNAF_OK;
 }
@@ -220,9 +237,13 @@ uint32_t raw_crc(const uint8_t* p, size_t n, const uint32_t* tab) {
     return c;
 }
 
-int ensure_fused(dnaf_ctx* c, const uint8_t* kk, const uint32_t* thr, const uint8_t* prefix, const uint64_t* pre_off) {
-    c->fused_ok = false;
+constexpr int kVariants = 10;  // tables per MAF bucket: auto+prefix, auto, then (class x {prefix, no prefix}) for k_fused_text
+
+// Called from set_snps: bucket every row by its first threshold, remember which prefix bytes occur.
+int prepare_buckets(dnaf_ctx* c, const uint8_t* kk, const uint32_t* thr, const uint8_t* prefix, const uint64_t* pre_off) {
     c->h_bucket.assign(c->S, 0);
+    c->bucket_p.clear();
+    c->tables_sig.clear();
     if (c->S == 0) return DNAF_OK;
     // bucket key: the first threshold (minor-allele probability = 1 - (T+1)/2^32), coarsened until <= 512 keys
     std::map<uint32_t, int> keys;
@@ -239,68 +260,115 @@ int ensure_fused(dnaf_ctx* c, const uint8_t* kk, const uint32_t* thr, const uint
     }
     int nb = 0;
     for (auto& kv : keys) kv.second = nb++;
+    c->bucket_p.resize(nb);
+    for (auto& kv : keys) {
+        const uint64_t lo = (uint64_t)kv.first << shift;
+        const uint64_t hi = std::min<uint64_t>(0xFFFFFFFFull, lo + ((1ull << shift) - 1));
+        const double t_mid = 0.5 * ((double)lo + (double)hi);
+        c->bucket_p[kv.second] = std::min(1.0, std::max(0.0, 1.0 - (t_mid + 1.0) / 4294967296.0));
+    }
     for (uint64_t r = 0; r < c->S; ++r) {
         const uint32_t t = kk[r] >= 2 ? thr[r * 4] : 0xFFFFFFFFu;
         c->h_bucket[r] = (uint16_t)keys[t >> shift];
     }
     // prefix byte model (x16 fixed point per row): which bytes occur, weighted by kind -- deliberately not the
     // exact counts, so that tables can be cached across set_snps calls with similar prefixes
-    std::vector<uint64_t> ph(256, 0);
+    c->ph.assign(256, 0);
     const uint64_t total = pre_off[c->S];
-    for (uint64_t i = 0; i < total; ++i) ph[prefix[i]] = 1;
-    uint64_t ph_hash = 1469598103934665603ull;
+    for (uint64_t i = 0; i < total; ++i) c->ph[prefix[i]] = 1;
+    c->ph_hash = 1469598103934665603ull;
     for (int b = 0; b < 256; ++b) {
-        if (ph[b]) ph[b] = b == '\t' ? 144 : ((b >= '0' && b <= '9') ? 24 : 16);
-        ph_hash = (ph_hash ^ ph[b]) * 1099511628211ull;
+        if (c->ph[b]) c->ph[b] = b == '\t' ? 144 : ((b >= '0' && b <= '9') ? 24 : 16);
+        c->ph_hash = (c->ph_hash ^ c->ph[b]) * 1099511628211ull;
     }
-    std::vector<FusedTable> tabs((size_t)nb * 2);
-    for (auto& kv : keys) {
-        const uint64_t lo = (uint64_t)kv.first << shift;
-        const uint64_t hi = std::min<uint64_t>(0xFFFFFFFFull, lo + ((1ull << shift) - 1));
-        const double t_mid = 0.5 * ((double)lo + (double)hi);
-        const double p_minor = std::min(1.0, std::max(0.0, 1.0 - (t_mid + 1.0) / 4294967296.0));
+    return DNAF_OK;
+}
+
+// Called from ensure_layout (samples and SNPs known): static Huffman tables for every (bucket, variant) in use.
+int ensure_tables(dnaf_ctx* c) {
+    c->fused_ok = false;
+    if (c->S == 0 || c->n == 0) return DNAF_OK;
+    const int nb = (int)c->bucket_p.size();
+    std::vector<uint8_t> need((size_t)nb * kVariants, 0);
+    for (uint64_t r = 0; r < c->S; ++r) {
+        const int b = c->h_bucket[r];
+        if (c->h_cls[r] == kAuto && c->h_k[r] <= 2) {
+            need[b * kVariants + 0] = need[b * kVariants + 1] = 1;
+        } else {
+            need[b * kVariants + 2 + 2 * c->h_cls[r]] = need[b * kVariants + 3 + 2 * c->h_cls[r]] = 1;
+        }
+    }
+    std::vector<uint64_t> sig;
+    sig.reserve(need.size() + 2);
+    sig.push_back(c->ph_hash);
+    sig.push_back(c->samples_epoch);
+    for (int b = 0; b < nb; ++b) {
         uint64_t pbits;
-        memcpy(&pbits, &p_minor, 8);
-        auto cached = [&](uint64_t variant, const uint64_t* hist) -> const FusedTable& {
-            auto key = std::make_pair(pbits, variant);
-            auto it = c->table_cache.find(key);
-            if (it == c->table_cache.end()) it = c->table_cache.emplace(key, hosttab::make_table(p_minor, hist)).first;
-            return it->second;
-        };
-        tabs[2 * kv.second] = cached(ph_hash, ph.data());   // segments that carry the row prefix
-        tabs[2 * kv.second + 1] = cached(0, nullptr);       // the others
-        if (tabs[2 * kv.second].hdr_bits == 0xFFFFFFFFu || tabs[2 * kv.second + 1].hdr_bits == 0xFFFFFFFFu) return DNAF_OK;
+        memcpy(&pbits, &c->bucket_p[b], 8);
+        for (int v = 0; v < kVariants; ++v) sig.push_back(need[b * kVariants + v] ? pbits : 0);
     }
-    int rc = upload(c, c->d_ftables, tabs.data(), tabs.size());
-    if (rc) return rc;
-    if (c->etab_ok) {
-        c->fused_ok = true;
-        return DNAF_OK;
-    }
-    // E tables: contribution of mask byte b at byte k of word w to the span's linear CRC (span end aligned)
-    std::vector<uint32_t> tab(256), xp(257);
-    for (uint32_t i = 0; i < 256; ++i) {
-        uint32_t v = i;
-        for (int k = 0; k < 8; ++k) v = (v & 1u) ? (v >> 1) ^ kCrcPoly : (v >> 1);
-        tab[i] = v;
-    }
-    xp[0] = 0x80000000u;
-    for (int k = 1; k <= 256; ++k) xp[k] = hosttab::mulmod(xp[k - 1], 0x00800000u);
-    std::vector<uint32_t> etab(16 * 256, 0);
-    for (int w = 0; w < 4; ++w)
-        for (int k = 0; k < 4; ++k)
-            for (int b = 0; b < 256; ++b) {
-                uint32_t v = 0;
-                for (int i = 0; i < 8; ++i)
-                    if ((b >> i) & 1) {
-                        const int j = 32 * w + 8 * k + i;             // allele slot, byte 2j of the span
-                        v ^= hosttab::mulmod(xp[255 - 2 * j], tab[1]);
-                    }
-                etab[(4 * w + k) * 256 + b] = v;
+    if (sig != c->tables_sig) {
+        std::vector<FusedTable> tabs((size_t)nb * kVariants);
+        memset(tabs.data(), 0, tabs.size() * sizeof(FusedTable));
+        for (int b = 0; b < nb; ++b) {
+            const double p = c->bucket_p[b];
+            uint64_t pbits;
+            memcpy(&pbits, &p, 8);
+            for (int v = 0; v < kVariants; ++v) {
+                if (!need[b * kVariants + v]) continue;
+                const bool with_prefix = (v & 1) == 0;
+                const int cls = v < 2 ? -1 : (v - 2) / 2;
+                const uint64_t vkey = (with_prefix ? c->ph_hash : 0x5bd1e995ull) * 31 + (uint64_t)(cls + 1) * 1000003ull +
+                                      (cls >= 0 ? c->samples_epoch * 0x9E3779B97F4A7C15ull : 0);
+                auto key = std::make_pair(pbits, vkey);
+                auto it = c->table_cache.find(key);
+                if (it == c->table_cache.end()) {
+                    const uint64_t* hist = with_prefix ? c->ph.data() : nullptr;
+                    FusedTable t = cls < 0 ? hosttab::make_table(p, hist)
+                                           : hosttab::make_text_table(cls, p, c->h_sex.data(), c->n, hist);
+                    if (t.hdr_bits == 0xFFFFFFFFu) return DNAF_OK;  // header too long: stay on the generic path
+                    it = c->table_cache.emplace(key, t).first;
+                }
+                tabs[(size_t)b * kVariants + v] = it->second;
             }
-    rc = upload(c, c->d_etab, etab.data(), etab.size());
-    if (rc) return rc;
-    c->etab_ok = true;
+        }
+        int rc = upload(c, c->d_ftables, tabs.data(), tabs.size());
+        if (rc) return rc;
+        c->tables_sig = sig;
+    }
+    if (!c->etab_ok) {
+        // E tables: contribution of mask byte b at byte k of word w to the span's linear CRC (span end aligned)
+        std::vector<uint32_t> tab(256), xp(257);
+        for (uint32_t i = 0; i < 256; ++i) {
+            uint32_t v = i;
+            for (int k = 0; k < 8; ++k) v = (v & 1u) ? (v >> 1) ^ kCrcPoly : (v >> 1);
+            tab[i] = v;
+        }
+        xp[0] = 0x80000000u;
+        for (int k = 1; k <= 256; ++k) xp[k] = hosttab::mulmod(xp[k - 1], 0x00800000u);
+        std::vector<uint32_t> etab(16 * 256, 0);
+        for (int w = 0; w < 4; ++w)
+            for (int k = 0; k < 4; ++k)
+                for (int b = 0; b < 256; ++b) {
+                    uint32_t v = 0;
+                    for (int i = 0; i < 8; ++i)
+                        if ((b >> i) & 1) {
+                            const int j = 32 * w + 8 * k + i;             // allele slot, byte 2j of the span
+                            v ^= hosttab::mulmod(xp[255 - 2 * j], tab[1]);
+                        }
+                    etab[(4 * w + k) * 256 + b] = v;
+                }
+        int rc = upload(c, c->d_etab, etab.data(), etab.size());
+        if (rc) return rc;
+        // slicing-by-4 tables for k_fused_text
+        std::vector<uint32_t> c4(1024);
+        for (int i = 0; i < 256; ++i) c4[i] = tab[i];
+        for (int t = 1; t < 4; ++t)
+            for (int i = 0; i < 256; ++i) c4[256 * t + i] = (c4[256 * (t - 1) + i] >> 8) ^ tab[c4[256 * (t - 1) + i] & 0xFFu];
+        rc = upload(c, c->d_crc4, c4.data(), c4.size());
+        if (rc) return rc;
+        c->etab_ok = true;
+    }
     c->fused_ok = true;
     return DNAF_OK;
 }
@@ -311,6 +379,7 @@ void build_segments(dnaf_ctx* c) {
     c->h_seg_cell0.clear();
     c->h_seg_crc.clear();
     c->fused_threads = 64;
+    for (auto& v : c->seg_byte0) v.clear();
     if (c->n == 0) return;
     std::vector<uint32_t> tab(256);
     for (uint32_t i = 0; i < 256; ++i) {
@@ -333,16 +402,33 @@ void build_segments(dnaf_ctx* c) {
     }
     c->h_seg_cell0.push_back(c->n);
     c->fused_threads = std::max(64u, (per + 31u) / 32u * 32u);
+    // k_fused_text: balanced byte segments (multiples of 256 bytes) of every class body
+    c->text_threads = 64;
+    for (int cls = 0; cls < 4; ++cls) {
+        c->seg_byte0[cls].clear();
+        const uint32_t body = c->body[cls];
+        const uint32_t sp = (body + 255u) / 256u;
+        const uint32_t ns = (sp + 253u) / 254u;
+        const uint32_t pr = (sp + ns - 1u) / ns;
+        for (uint32_t sg = 0; sg < ns; ++sg)
+            if (sg * pr * 256u < body) c->seg_byte0[cls].push_back(sg * pr * 256u);
+        c->seg_byte0[cls].push_back(body);
+        c->text_threads = std::max(c->text_threads, (pr + 31u) / 32u * 32u);
+    }
 }
 
-inline bool row_is_fused(const dnaf_ctx* c, uint64_t r, const uint8_t* hk) {
-    return c->fused && c->fused_ok && c->h_cls[r] == kAuto && hk[r] <= 2 && c->h_plen[r] >= 1 && c->h_plen[r] <= 64 &&
-           4ull * c->n >= kFusedMinRowBytes;
+// 0 = generic three-kernel path, 1 = k_fused_auto, 2 = k_fused_text
+inline int row_kind(const dnaf_ctx* c, uint64_t r, const uint8_t* hk) {
+    if (!c->fused || !c->fused_ok || c->h_plen[r] < 1 || c->h_plen[r] > 64 || c->n == 0) return 0;
+    if (c->body[c->h_cls[r]] < kFusedMinRowBytes) return 0;
+    return (c->h_cls[r] == kAuto && hk[r] <= 2) ? 1 : 2;
 }
+inline bool row_is_fused(const dnaf_ctx* c, uint64_t r, const uint8_t* hk) { return row_kind(c, r, hk) != 0; }
 
 // BGZF block plan of one pass (rows [r0,r1)): fused segments and generic blocks, slots in row order.
 void plan_pass(dnaf_ctx* c, uint64_t r0, uint64_t r1, const uint8_t* hk) {
     c->fplan.clear();
+    c->tplan.clear();
     c->plan.clear();
     c->gslot.clear();
     c->grow.clear();
@@ -355,7 +441,30 @@ void plan_pass(dnaf_ctx* c, uint64_t r0, uint64_t r1, const uint8_t* hk) {
     uint64_t r = r0;
     while (r < r1) {
         while (o < c->h_orow.size() && c->h_orow[o] < r) ++o;
-        if (row_is_fused(c, r, hk)) {
+        const int kind = row_kind(c, r, hk);
+        if (kind == 2) {
+            size_t oe = o;
+            while (oe < c->h_orow.size() && c->h_orow[oe] == r) ++oe;
+            const std::vector<uint32_t>& sb = c->seg_byte0[c->h_cls[r]];
+            const size_t nseg = sb.size() - 1;
+            for (size_t sgi = 0; sgi < nseg; ++sgi) {
+                TextDesc d;
+                d.row = r;
+                d.byte0 = sb[sgi];
+                d.nbytes = sb[sgi + 1] - sb[sgi];
+                d.slot = slot++;
+                d.flags = (sgi == 0 ? 1u : 0u) | (sgi + 1 == nseg ? 2u : 0u);
+                d.ovr_first = (uint32_t)o;
+                d.ovr_count = (uint32_t)(oe - o);
+                d.table = (uint32_t)c->h_bucket[r] * kVariants + 2u + 2u * c->h_cls[r] + (sgi == 0 ? 0u : 1u);
+                d.pad = 0;
+                c->tplan.push_back(d);
+            }
+            o = oe;
+            ++r;
+            continue;
+        }
+        if (kind == 1) {
             size_t oe = o;
             while (oe < c->h_orow.size() && c->h_orow[oe] == r) ++oe;
             const size_t nseg = c->h_seg_crc.size();
@@ -368,7 +477,7 @@ void plan_pass(dnaf_ctx* c, uint64_t r0, uint64_t r1, const uint8_t* hk) {
                 d.flags = (sgi == 0 ? 1u : 0u) | (sgi + 1 == nseg ? 2u : 0u);
                 d.ovr_first = (uint32_t)o;
                 d.ovr_count = (uint32_t)(oe - o);
-                d.table = 2u * c->h_bucket[r] + (sgi == 0 ? 0u : 1u);
+                d.table = (uint32_t)c->h_bucket[r] * kVariants + (sgi == 0 ? 0u : 1u);
                 d.body_crc = c->h_seg_crc[sgi];
                 c->fplan.push_back(d);
             }
@@ -614,6 +723,36 @@ int generate_impl(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t se
         rc = launch_generic(c, &local);
         if (rc) return rc;
         CU(c, cudaEventRecord(c->ev[3], c->stream));
+        if (!c->tplan.empty()) {
+            rc = upload_async(c, c->d_tdesc, c->tplan);
+            if (rc) return rc;
+            if (!c->text_attr_done) {
+                CU(c, cudaFuncSetAttribute(k_fused_text, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TextSmem)));
+                c->text_attr_done = true;
+            }
+            TextArgs ta;
+            ta.sv = sample_view(c);
+            ta.nv = snp_view(c);
+            ta.desc = c->d_tdesc.as<TextDesc>();
+            ta.tables = c->d_ftables.as<FusedTable>();
+            ta.crc4 = c->d_crc4.as<uint32_t>();
+            ta.xpow8 = c->d_xpow8.as<uint32_t>();
+            ta.osamp = c->d_osamp.as<uint32_t>();
+            ta.xspan = c->d_xspan.as<uint32_t>();
+            ta.row_base = c->row_base;
+            ta.k0 = (uint32_t)seed;
+            ta.k1 = (uint32_t)(seed >> 32);
+            ta.slots = c->d_slots.as<uint8_t>();
+            ta.sizes = c->d_sizes.as<uint32_t>();
+            ta.crcs = c->d_crcs.as<uint32_t>();
+            // few, long blocks: start them first on the side stream so that k_fused_auto fills the rest of the chip
+            CU(c, cudaEventRecord(c->ev_fork, c->stream));
+            CU(c, cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+            k_fused_text<<<(uint32_t)c->tplan.size(), c->text_threads, sizeof(TextSmem), c->side>>>(ta);
+            CU(c, cudaEventRecord(c->ev_join, c->side));
+            local.kernel_launches += 1;
+            CU(c, cudaGetLastError());
+        }
         if (!c->fplan.empty()) {
             rc = upload_async(c, c->d_fdesc, c->fplan);
             if (rc) return rc;
@@ -637,6 +776,7 @@ int generate_impl(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t se
             local.kernel_launches += 1;
             CU(c, cudaGetLastError());
         }
+        if (!c->tplan.empty()) CU(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
         CU(c, cudaEventRecord(c->ev[4], c->stream));
         rc = finish_pass(c, c->pass_blocks, sink, &local);
         if (rc) return rc;
@@ -652,7 +792,7 @@ int generate_impl(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t se
             local.ms_format += t12;
         }
         local.ms_deflate += (c->plan.empty() ? 0.f : t23) + t45;
-        if (!c->fplan.empty()) local.ms_fused += t34;
+        if (!c->fplan.empty() || !c->tplan.empty()) local.ms_fused += t34;
         local.ms_total += t05;
         local.rows += r1 - r0;
         local.text_bytes += c->h_row_off[r1] - c->h_row_off[r0];
@@ -693,6 +833,13 @@ int dnaf_create(int device_ordinal, dnaf_ctx** out) {
     c->own_stream = true;
     for (auto& ev : c->ev)
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
+    {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if ((e = cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, hi)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    }
+    if ((e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     // CRC tables: byte table and x^(8k) mod P for k = 0..kBlk
     std::vector<uint32_t> tab(256), xp(kBlk + 1);
     for (uint32_t i = 0; i < 256; ++i) {
@@ -719,6 +866,9 @@ void dnaf_destroy(dnaf_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto& ev : c->ev)
         if (ev) cudaEventDestroy(ev);
+    if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -777,6 +927,19 @@ int dnaf_set_samples(dnaf_ctx* c, uint32_t n, const uint8_t* sex, const uint8_t*
     int rc = upload(c, c->d_sex, sex, n);
     if (!rc) rc = upload(c, c->d_xoff, xoff.data(), xoff.size());
     if (rc) return rc;
+    c->h_sex.assign(sex, sex + n);
+    c->samples_epoch++;
+    {   // X rows: the sample that holds body byte 256*k (for k_fused_text)
+        std::vector<uint32_t> xspan((size_t)acc / 256 + 2, 0);
+        uint32_t i = 0;
+        for (size_t k = 0; k < xspan.size(); ++k) {
+            const uint64_t byte = 256ull * k;
+            while (i + 1 < n && xoff[i + 1] <= byte) ++i;
+            xspan[k] = i;
+        }
+        rc = upload(c, c->d_xspan, xspan.data(), xspan.size());
+        if (rc) return rc;
+    }
     c->have_samples = true;
     c->layout_ok = false;
     return DNAF_OK;
@@ -819,7 +982,7 @@ int dnaf_set_snps(dnaf_ctx* c, uint64_t S, const uint8_t* cls, const uint8_t* k,
     }
     c->have_snps = true;
     c->layout_ok = false;
-    rc = ensure_fused(c, k, thr, prefix, pre_off);
+    rc = prepare_buckets(c, k, thr, prefix, pre_off);
     if (rc) return rc;
     return DNAF_OK;
 }

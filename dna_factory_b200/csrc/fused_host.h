@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "k_fused.cuh"
+#include "k_fused_text.cuh"
 
 namespace dnaf {
 namespace hosttab {
@@ -226,6 +227,83 @@ inline FusedTable make_table(double p_minor, const uint64_t* prefix_hist /* [256
     t.hdr_bits = hdr.bits;
     for (size_t i = 0; i < hdr.words.size() && i < 62; ++i) t.hdr[i] = hdr.words[i];
     if (hdr.words.size() > 62) t.hdr_bits = 0xFFFFFFFFu;  // caller treats as "no table" (cannot happen: < 1 KiB)
+    return t;
+}
+
+
+struct ByteHist {
+    uint64_t nlit[256] = {0};
+    uint64_t nlen[29] = {0};
+    void lit_byte(uint8_t b) { nlit[b]++; }
+    void match(int l) { nlen[len_index(l)]++; }
+};
+
+// Table for k_fused_text: token statistics of rows of chromosome class `cls` whose alleles are
+// Bernoulli(p_minor), laid out with the population's real sex vector (cell widths / '.' depend on it).
+inline FusedTable make_text_table(int cls, double p_minor, const uint8_t* sex, uint32_t n,
+                                  const uint64_t* prefix_hist) {
+    ByteHist h;
+    uint64_t st = 0xD1B54A32D192ED03ull ^ (uint64_t)(p_minor * 1e9) ^ ((uint64_t)cls << 56);
+    auto next = [&]() {
+        st ^= st << 13; st ^= st >> 7; st ^= st << 17;
+        return st;
+    };
+    const uint64_t thr = (uint64_t)(std::min(p_minor, 0.999999) * 18446744073709551615.0);
+    const uint32_t ns = std::min<uint32_t>(n, 32768);
+    const int reps = ns < 8192 ? 4 : 2;
+    uint64_t blocks = 0;
+    std::vector<uint8_t> text;
+    for (int rep = 0; rep < reps; ++rep) {
+        text.clear();
+        for (uint32_t i = 0; i < ns; ++i) {
+            const bool male = sex[i] == 1;
+            const bool wide = cls == kAuto || (cls == kX && !male);
+            const uint8_t a0 = '0' + (next() < thr), a1 = '0' + (next() < thr);
+            text.push_back((cls == kY && !male) ? '.' : a0);
+            if (wide) { text.push_back('/'); text.push_back(a1); }
+            text.push_back('\t');
+        }
+        while (text.size() % 4) text.push_back(0);
+        const uint32_t* words = reinterpret_cast<const uint32_t*>(text.data());
+        const size_t total = (size_t)ns * 0 + text.size();
+        size_t pos = 0;
+        int span_in_block = 0;
+        while (pos < total) {
+            const int nb = (int)std::min<size_t>(256, total - pos);
+            const uint32_t* w = words + pos / 4;
+            auto wat = [&](int k) { return w[k]; };
+            tokenize_words(wat, nb, span_in_block > 0, span_in_block > 0 ? w[-1] : 0u, h);
+            pos += nb;
+            if (++span_in_block == 254) { span_in_block = 0; ++blocks; }
+        }
+        ++blocks;
+    }
+    std::vector<uint64_t> f(286, 0);
+    const uint64_t scale = 16;
+    for (int c = 0; c < 256; ++c)
+        if (h.nlit[c]) f[c] += (h.nlit[c] * scale) / blocks + 1;
+    for (const char* c = "0123./\t\n"; *c; ++c) f[(uint8_t)*c] += 1;
+    for (int i = 0; i < 29; ++i) f[257 + i] += (h.nlen[i] * scale) / blocks + 1;
+    f[256] = scale;
+    if (prefix_hist)
+        for (int c = 0; c < 256; ++c)
+            if (prefix_hist[c]) f[c] += std::max<uint64_t>(1, prefix_hist[c]);
+    std::vector<uint8_t> ll = huff_lengths(f, 15);
+    std::vector<uint32_t> lc = huff_codes(ll);
+    FusedTable t;
+    memset(&t, 0, sizeof t);
+    for (int len = 3; len <= 258; ++len) {
+        const int ci = len_index(len);
+        const uint32_t c = lc[257 + ci];
+        const uint32_t cl = c >> 24, ex = (uint32_t)kLenExtra[ci];
+        t.len_tok[len] = ((c & 0xFFFFFFu) | ((uint32_t)(len - kLenBase[ci]) << cl)) | ((cl + ex + 1u) << 24);
+    }
+    t.eob = lc[256];
+    for (int c = 0; c < 256; ++c) t.pre_lit[c] = lc[c];
+    BitString hdr = dynamic_header(ll);
+    t.hdr_bits = hdr.bits;
+    for (size_t i = 0; i < hdr.words.size() && i < 62; ++i) t.hdr[i] = hdr.words[i];
+    if (hdr.words.size() > 62) t.hdr_bits = 0xFFFFFFFFu;
     return t;
 }
 

@@ -158,6 +158,16 @@ class SnpTable:
         return SnpTable(self.ids[order], self.chrom_idx[order], self.chrom_labels, self.position[order],
                         self.n_alleles[order], self.nts[order], self.cum[order])
 
+    @classmethod
+    def concat(cls, tables):
+        labels = tables[0].chrom_labels
+        if any(t.chrom_labels != labels for t in tables):
+            raise ValueError("tables use different chromosome label lists")
+        cat = np.concatenate
+        return cls(cat([t.ids for t in tables]), cat([t.chrom_idx for t in tables]), labels,
+                   cat([t.position for t in tables]), cat([t.n_alleles for t in tables]), cat([t.nts for t in tables]),
+                   cat([t.cum for t in tables]))
+
     def sorted(self):
         """Order of `ordered_snps.sort(key=lambda x: (x.chromosome, x.position))` (pop_factory.py:245):
         chromosome compared as a STRING, ties keep insertion order (stable)."""

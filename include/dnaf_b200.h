@@ -73,7 +73,7 @@ int dnaf_create(int device_ordinal, dnaf_ctx** out);
 void dnaf_destroy(dnaf_ctx* ctx);
 /* Launch on a caller-provided cudaStream_t (e.g. torch's current stream) instead of the private one. */
 int dnaf_set_stream(dnaf_ctx* ctx, void* cuda_stream);
-/* Upper bound on the uncompressed text handled per internal pass (default 256 MiB; tests shrink it). */
+/* Upper bound on the uncompressed text handled per internal pass (default 1 GiB; tests shrink it). */
 int dnaf_set_chunk_bytes(dnaf_ctx* ctx, uint64_t text_bytes);
 /* Philox row counter of local row r is row_base + r (default 0): lets a process that holds only a slice
  * of the sorted SNP list, e.g. one rank of a multi-GPU run, draw the rows it was given. */

@@ -40,7 +40,7 @@ def load_case(name):
                            text=text)
 
 
-def synth_case(n_samples, n_snps, seed=1, male_odds=0.5, chroms=None, n_case_frac=0.5, n_del=3):
+def synth_case(n_samples, n_snps, seed=1, male_odds=0.5, chroms=None, n_case_frac=0.5, n_del=3, exotic=False):
     """Seeded synthetic population shaped like SnpFactory output (biallelic, MAF grid) for oracle-vs-CUDA tests."""
     import numpy as np
     rs = np.random.RandomState(seed)
@@ -51,7 +51,14 @@ def synth_case(n_samples, n_snps, seed=1, male_odds=0.5, chroms=None, n_case_fra
         maf = (1 + rs.randint(99)) * 0.005
         nts = ["A", "T", "C", "G"]
         rs.shuffle(nts)
-        snps.append(Snp(id=i + 1, chromosome=c, position=int(rs.rand() * 5e7), tuples=[(nts[0], 1 - maf), (nts[1], 1.0)]))
+        tup = [(nts[0], 1 - maf), (nts[1], 1.0)]
+        if exotic and i % 5 == 1:
+            tup = [(nts[0], 0.55), (nts[1], 0.8), (nts[2], 1.0)]
+        elif exotic and i % 5 == 2:
+            tup = [(nts[0], 0.4), (nts[1], 0.7), (nts[2], 0.9), (nts[3], 1.0)]
+        elif exotic and i % 5 == 3:
+            tup = [(nts[0], 1.0)]
+        snps.append(Snp(id=i + 1, chromosome=c, position=int(rs.rand() * 5e7), tuples=tup))
     snps.sort(key=lambda x: (x.chromosome, x.position))
     n_ctl = int(n_samples * (1 - n_case_frac))
     samples = []

@@ -124,6 +124,24 @@ def test_fused_kernel_vs_oracle_and_generic(native, n, s, seed):
     assert st_f["bgzf_bytes"] < 1.10 * st_p["bgzf_bytes"] + 4096
 
 
+@pytest.mark.parametrize("n,s,seed,odds", [(8192, 16, 41, 0.5), (8193, 16, 42, 0.5), (9000, 12, 43, 0.0),
+                                           (9000, 12, 44, 1.0), (20000, 20, 45, 0.5), (40000, 8, 46, 0.3)])
+def test_fused_text_kernel_all_classes(native, n, s, seed, odds):
+    """X / Y / MT rows and multi-allelic autosome rows go through k_fused_text (text staged in shared memory)."""
+    from oracle import oracle
+    case = synth_case(n, s, seed=seed, male_odds=odds, chroms=['X', 'Y', 'MT', '3', 'X'], n_del=60, exotic=True)
+    want, _ = oracle.rows(case.samples, case.snps, case.seed, 0, n_threads=4)
+    eng = _engine(native, case, chunk=16 << 20)
+    fused, st_f = eng.generate(0, s, case.seed, level=2)
+    assert st_f["ms_fused"] > 0 and st_f["ms_sample"] == 0
+    assert oracle.bgzf_decompress(fused)[0] == want
+    eng.set_fused(False)
+    plain, st_p = eng.generate(0, s, case.seed, level=2)
+    assert oracle.bgzf_decompress(plain)[0] == want
+    # rows with 3-4 alleles share the biallelic MAF buckets, so the static codes fit them less well
+    assert st_f["bgzf_bytes"] < 1.35 * st_p["bgzf_bytes"] + 8192
+
+
 def test_bgzf_compress_arbitrary_bytes(native):
     from oracle import oracle
     _native, _ = native
