@@ -67,14 +67,16 @@ def synth_population(n_rows, rank=0, window=ROWS_PER_STEP):
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons of one GPU while the timed region runs."""
+    """Samples SM clock and throttle reasons of one GPU; started before the warm-up so that NVML is up when the
+    timed region begins, reports the samples that fall inside [mark_begin, mark_end]."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
-        self.samples = []
-        self.reasons = set()
+        self.samples = []          # (time, sm_mhz, reason bits)
         self.max_mhz = None
+        self.error = None
+        self.t0 = self.t1 = None
         self._stop_evt = threading.Event()
 
     def run(self):
@@ -83,26 +85,35 @@ class ClockSampler(threading.Thread):
             nv.nvmlInit()
             h = nv.nvmlDeviceGetHandleByIndex(self.index)
             self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
-                     "hw_power_brake_slowdown": 0x80}
             while not self._stop_evt.is_set():
-                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
                 try:
                     r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
                 except Exception:
                     r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for k, bit in names.items():
-                    if r & bit:
-                        self.reasons.add(k)
-                time.sleep(0.05)
+                self.samples.append((time.perf_counter(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), r))
+                time.sleep(0.002)
         except Exception as e:  # noqa: clocks are reported as unknown, never fatal
-            self.reasons.add("unavailable:%s" % type(e).__name__)
+            self.error = "unavailable:%s" % type(e).__name__
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=2)
-        med = float(np.median(self.samples)) if self.samples else None
-        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake_slowdown": 0x80}
+        inside = [x for x in self.samples if self.t0 is not None and self.t0 <= x[0] <= self.t1]
+        if not inside and self.samples and self.t0 is not None:   # region shorter than the poll interval
+            inside = [min(self.samples, key=lambda x: abs(x[0] - 0.5 * (self.t0 + self.t1)))]
+        reasons = sorted({k for x in inside for k, bit in names.items() if x[2] & bit})
+        if self.error:
+            reasons.append(self.error)
+        return {"sm_mhz": float(np.median([x[1] for x in inside])) if inside else None, "sm_max_mhz": self.max_mhz,
+                "reasons": reasons, "samples": len(inside)}
 
 
 def cpu_reference_run(steps, warmup, budget_s=20.0):
@@ -175,7 +186,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from dna_factory_b200 import _native
+    from dna_factory_b200 import _native, partition
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: dna_factory_b200 has no CPU fallback")
@@ -190,7 +201,7 @@ def main():
     sex, ctl, table, orow, osamp = synth_population(rows_needed, rank, window=R)
     arrays = table.device_arrays()
     n = len(sex)
-    row_base = rank * (TOTAL_SNPS // max(world, 1))
+    row_base = partition.row_bounds(TOTAL_SNPS, world)[rank]   # this rank's contiguous SNP range of the job
 
     eng = _native.Engine(local_rank)
     stream = torch.cuda.current_stream()
@@ -207,25 +218,18 @@ def main():
         torch.cuda.synchronize()
 
     def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return partition.reduce_max(x, dist if world > 1 else None, "cuda")
 
     def sum_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+        return partition.reduce_sum(x, dist if world > 1 else None, "cuda")
 
     # ------------------------------------------------------------------ device-resident pass (`value`)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for k in range(warmup):
         eng.generate_device(k * R, (k + 1) * R, PHILOX_SEED, level=LEVEL)
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.mark_begin()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stats = []
     ev0.record(stream)
@@ -233,6 +237,7 @@ def main():
         stats.append(eng.generate_device(k * R, (k + 1) * R, PHILOX_SEED, level=LEVEL))
     ev1.record(stream)
     barrier()
+    sampler.mark_end()
     clocks = sampler.stop()
     ms = max_over_ranks(ev0.elapsed_time(ev1))
     calls = sum_over_ranks(sum(s["calls"] for s in stats))

@@ -106,6 +106,31 @@ def override_pairs(fam_data, snps, row_base=0):
     return np.asarray(rows, dtype=np.uint64), np.asarray(samples, dtype=np.uint32)
 
 
+def override_pairs_table(fam_data, table, row_base=0):
+    """override_pairs for a SnpTable (integer ids): same membership semantics, no per-SNP Python objects.
+    A key matches a row when `row_id in {key: ...}` would, i.e. when the key is a number equal to the id
+    (string keys of a deleterious.json replay never equal an int id)."""
+    ids = table.ids
+    order = np.argsort(ids, kind="stable")
+    sorted_ids = ids[order]
+    rows, samples = [], []
+    for i, s in enumerate(fam_data):
+        if s.is_control or not s.deleterious_snps:
+            continue
+        for key in s.deleterious_snps.keys():
+            if isinstance(key, bool) or not isinstance(key, (int, float, np.integer, np.floating)) or key != int(key):
+                continue
+            lo = np.searchsorted(sorted_ids, int(key), side="left")
+            hi = np.searchsorted(sorted_ids, int(key), side="right")
+            for r in order[lo:hi]:
+                rows.append(row_base + int(r))
+                samples.append(i)
+    rows = np.asarray(rows, dtype=np.uint64)
+    samples = np.asarray(samples, dtype=np.uint32)
+    o = np.lexsort((samples, rows))
+    return rows[o], samples[o]
+
+
 def configure(engine, fam_data, snps):
     """Load a population (samples, sorted SNP list, overrides) into an Engine."""
     sex, ctl = flatten_samples(fam_data)

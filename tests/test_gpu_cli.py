@@ -1,0 +1,70 @@
+"""GPU end-to-end test of the re-hosted CLI against the reference CLI run pinned in tests/golden/cli_small."""
+import gzip
+import json
+import os
+import random
+
+import pytest
+
+from tests.cases import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(tmp_path, monkeypatch, extra):
+    from dna_factory_b200 import pop_factory
+    gold = os.path.join(GOLDEN, "cli_small")
+    meta = json.load(open(os.path.join(gold, "meta.json")))
+
+    class FixedDatetime(pop_factory.datetime):
+        @classmethod
+        def now(cls, tz=None):
+            return cls(2026, 1, 1, 12, 34, 56)
+
+    monkeypatch.setattr(pop_factory, "datetime", FixedDatetime)
+    random.seed(meta["python_random_seed"])
+    args = meta["args"] + ["-p", os.path.join(gold, "deleterious_config.yml"), "--outdir", str(tmp_path),
+                           "--seed", str(meta["philox_seed"])] + extra
+    pop_factory.main(args)
+    return gold, meta
+
+
+@pytest.mark.parametrize("extra", [[], ["--gpus", "1", "-n", "7"]])
+def test_cli_output_directory_matches_reference(tmp_path, monkeypatch, extra):
+    """Every file the reference writes, byte for byte (population.vcf.gz: its decompressed bytes)."""
+    import hashlib
+    from oracle import oracle
+    gold, meta = _run(tmp_path, monkeypatch, extra)
+    blob = (tmp_path / "population.vcf.gz").read_bytes()
+    vcf = gzip.decompress(blob)
+    assert hashlib.sha256(vcf).hexdigest() == meta["vcf_sha256"] and len(vcf) == meta["vcf_len"]
+    text, blocks, eof = oracle.bgzf_decompress(blob)
+    assert text == vcf and eof and blocks >= 3
+    with gzip.open(tmp_path / "snps.json.gz", "rb") as f:
+        assert f.read() == open(os.path.join(gold, "snps.json"), "rb").read()
+    for name in ("deleterious.json", "population.fam", "pop_deleterious.txt"):
+        assert (tmp_path / name).read_bytes() == open(os.path.join(gold, name), "rb").read(), name
+
+
+def test_cli_replay_from_files_reproduces_r8(tmp_path, monkeypatch):
+    """--snps_file / --deleterious_file replay: string keys of deleterious.json never match the int ids, so
+    no forced minors appear -- exactly what the reference does.  Checked against the oracle."""
+    from dna_factory_b200 import pop_factory
+    from dna_factory_b200.snp import SnpTable
+    from oracle import oracle
+    gold, meta = _run(tmp_path, monkeypatch, [])
+    out2 = tmp_path / "replay"
+    random.seed(99)
+    pop_factory.main(["-s", "5", "-c", "4", "-z", "2", "--snps_file", str(tmp_path / "snps.json.gz"),
+                      "--deleterious_file", str(tmp_path / "deleterious.json"), "--outdir", str(out2), "--seed", "77"])
+    vcf = gzip.decompress((out2 / "population.vcf.gz").read_bytes())
+    header, rows = vcf.split(b"\n", 6)[:6], vcf.split(b"\n", 6)[6]
+    snps = SnpTable.read_json_gz(str(tmp_path / "snps.json.gz"))
+    fam = []
+    for line in (out2 / "population.fam").read_text().splitlines():
+        f = line.split("\t")
+        fam.append(pop_factory.SampleInfo(int(f[0]), int(f[1]), 0, 0, int(f[4]), f[5] == "1",
+                                          None if f[5] == "1" else {"not-an-int-key": 1}))
+    want, _ = oracle.rows(fam, snps, 77, 0)
+    assert rows == want
+    assert len(header) == 6

@@ -1,0 +1,164 @@
+"""CPU tests of the host-side mirror of the reference interface (no GPU compute)."""
+import gzip
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+from tests.cases import GOLDEN, load_case
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    import re
+    from dna_factory_b200 import _native, build
+    build.build()
+    lib = _native.load()
+    header = open(os.path.join(os.path.dirname(GOLDEN), "..", "include", "dnaf_b200.h")).read()
+    declared = set(re.findall(r"\b(dnaf_[a-z0-9_]+)\s*\(", header)) - {"dnaf_sink_fn"}
+    assert declared == set(_native.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.dnaf_abi_version() == 1
+    assert _native.bgzf_eof() == bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+
+
+def test_missing_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from dna_factory_b200 import _native
+    with pytest.raises(_native.DnafError) as e:
+        _native.Engine(0)
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_arg_parser_matches_reference_surface():
+    # test/unit/pop_factory_test.py:78-104
+    from dna_factory_b200 import pop_factory
+    cmd = ("-s 10 -c 20 -n 5 -z 3 -p path_config.yml -f 0.1 -m 0.7 -x 2500 -l "
+           "--deleterious_file /home/ochrzan/workspace/deleterious.json --offset 300 --snps_file my_snps.json "
+           "--outdir myoutput/tuesday")
+    a = pop_factory.parse_cmd_args(cmd.split(" "))
+    assert (a.size, a.control_size, a.num_processes, a.compression_level) == (10, 20, 5, 3)
+    assert (a.deleterious_config, a.min_freq, a.male_odds, a.max_snps) == ("path_config.yml", 0.1, 0.7, 2500)
+    assert a.generate_snps is False and a.offset == 300
+    assert a.deleterious_file == "/home/ochrzan/workspace/deleterious.json"
+    assert a.snps_file == "my_snps.json" and a.outdir == "myoutput/tuesday"
+    b = pop_factory.parse_cmd_args("-s 10 -c 20 -x 2500".split(" "))
+    assert b.deleterious_file is None and b.compression_level == 6 and b.num_processes == 2
+    assert b.deleterious_config == "deleterious.yml" and b.min_freq == 0.005 and b.male_odds == 0.5
+    assert b.generate_snps is True
+
+
+def test_snp_tuple_known_answers():
+    # test/unit/pop_factory_test.py:5-28
+    from dna_factory_b200.snp import SNPTuples
+    s = SNPTuples(100, "1", 50000)
+    for nt, c in (("G", 0.70), ("A", 0.90), ("T", 1.0)):
+        s.add_tuple(nt, c)
+    assert s.pick_snp_value(0.95) == "T" and s.pick_snp_value(0.4) == "G"
+    assert s.pick_allele_index(0.95) == 2 and s.pick_allele_index(0.4) == 0
+    assert s.alt_alleles() == "A,T"
+    assert SNPTuples.from_json(str(s)).tuples == s.tuples
+
+
+def test_split_list_and_ploidy():
+    # test/unit/common_util_test.py:7-12, common/snp.py:102-109
+    from dna_factory_b200.snp import is_haploid, split_list, stripe_list
+    y = list(split_list(list(range(100)), 3))
+    assert [len(v) for v in y] == [33, 33, 34]
+    assert stripe_list(list(range(7)), 3) == [[0, 3, 6], [1, 4], [2, 5]]
+    assert is_haploid("X", True) and not is_haploid("X", False)
+    assert is_haploid("Y", False) and is_haploid("MT", False) and not is_haploid("7", True)
+
+
+def test_deleterious_group_from_yml():
+    # test/unit/pop_factory_test.py:31-44
+    from dna_factory_b200.pop_factory import DeleteriousGroup
+    from dna_factory_b200.snp import SNPTuples
+    data = []
+    for i in range(1, 5):
+        s = SNPTuples(i, "1", 50000)
+        for nt, c in (("G", 0.70), ("A", 0.90), ("T", 1.0)):
+            s.add_tuple(nt, c)
+        data.append(s)
+    groups = DeleteriousGroup.from_yml({"mutation_weights": [0.5, 0.5, 0.5], "num_instances": 2,
+                                        "population_weight": 5, "min_minor_allele_freq": 0.01}, data, "groupA")
+    assert len(groups) == 2 and groups[0].population_weight == 5
+    assert len(groups[0].deleterious) == 3 and len(groups[0].select_mutations()) == 2
+
+
+def test_snp_factory_distribution():
+    # test/unit/snp_factory_test.py:14-37 (tolerances as upstream)
+    from dna_factory_b200.snp import CHROMOSOME_PROB, SnpFactory
+    np.random.seed(7)
+    random.seed(7)
+    fac = SnpFactory.init_from_cdf_file()
+    n, min_maf = 100000, 0.16
+    t = fac.random_snp_table(n, min_maf=min_maf)
+    assert len(t) == n and (t.n_alleles == 2).all()
+    largest = fac.sorted_maf[-1]
+    assert ((1 - t.cum[:, 0]) >= min_maf - 1e-12).all()
+    assert (t.nts[:, 0] != t.nts[:, 1]).all()
+    assert abs((t.cum[:, 0] == 1 - largest).mean() - fac.pdf[-1] / fac.pdf[fac._first_bin(min_maf):].sum()) < 0.01
+    assert abs((t.chrom_idx == 0).mean() - CHROMOSOME_PROB[0]) < 0.01
+
+
+def test_host_files_match_reference_cli_golden(tmp_path, monkeypatch):
+    """snps.json.gz, deleterious.json, population.fam and pop_deleterious.txt byte for byte against the
+    reference CLI run pinned in tests/golden/cli_small (the VCF itself needs the GPU: test_gpu_cli.py)."""
+    from dna_factory_b200 import pop_factory
+    gold = os.path.join(GOLDEN, "cli_small")
+    meta = json.load(open(os.path.join(gold, "meta.json")))
+
+    class FixedDatetime(pop_factory.datetime):
+        @classmethod
+        def now(cls, tz=None):
+            return cls(2026, 1, 1, 12, 34, 56)
+
+    monkeypatch.setattr(pop_factory, "datetime", FixedDatetime)
+    captured = {}
+
+    def fake_output(self, control_size, test_size, male_odds, level):
+        groups = pop_factory.PopulationFactory.pick_deleterious_groups(list(self.deleterious.values()), test_size)
+        captured["fam"] = self.generate_fam_file(control_size, test_size, male_odds, groups)
+        captured["header"] = pop_factory.gen_vcf_header(captured["fam"])
+
+    monkeypatch.setattr(pop_factory.PopulationFactory, "output_vcf_population", fake_output)
+    random.seed(meta["python_random_seed"])
+    args = meta["args"] + ["-p", os.path.join(gold, "deleterious_config.yml"), "--outdir", str(tmp_path)]
+    pop_factory.main(args)
+    with gzip.open(tmp_path / "snps.json.gz", "rb") as f:
+        assert f.read() == open(os.path.join(gold, "snps.json"), "rb").read()
+    for name in ("deleterious.json", "population.fam", "pop_deleterious.txt"):
+        assert (tmp_path / name).read_bytes() == open(os.path.join(gold, name), "rb").read(), name
+    with gzip.open(os.path.join(gold, "population.vcf.rows.gz"), "rb") as f:
+        vcf = f.read()
+    assert vcf.startswith(captured["header"].encode())
+
+
+def test_override_pairs_table_equals_object_path():
+    from dna_factory_b200 import host
+    from dna_factory_b200.snp import SnpTable
+    case = load_case("mixed64")
+    biallelic = [s for s in case.snps if len(s.tuples) <= 4]
+    table = SnpTable.from_snps(biallelic)
+    a = host.override_pairs(case.samples, biallelic)
+    b = host.override_pairs_table(case.samples, table)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and len(a[0]) > 0
+    r8 = load_case("r8_strkeys")
+    t8 = SnpTable.from_snps(r8.snps)
+    assert len(host.override_pairs_table(r8.samples, t8)[0]) == 0
+
+
+def test_threshold_is_exact_for_inclusive_compare():
+    from dna_factory_b200 import host
+    # cum >= U/2^32  <=>  U <= threshold(cum), checked around awkward values
+    for cum in (0.0, 2.0 ** -32, 0.3, 0.9299999999999999, 1 - 2.0 ** -32, 1 - 2.0 ** -33, 1.0, 1.5):
+        t = host.threshold(cum)
+        for U in {0, 1, max(t - 1, 0), t, min(t + 1, 0xFFFFFFFF), 0xFFFFFFFF}:
+            assert (cum >= U * 2.0 ** -32) == (U <= t), (cum, U)
+    with pytest.raises(ValueError):
+        host.threshold(-0.1)
