@@ -170,6 +170,11 @@ struct HistSink {
     uint64_t nlen[29] = {0};
     void lit(int id) { nlit[id]++; }
     void match(int l) { nlen[len_index(l)]++; }
+    void gap_lit(int gap, int odd, int bit) {
+        if (gap == 1) lit(odd ? kLitSlash : kLitTab);
+        else if (gap) match(gap);
+        lit(bit);
+    }
 };
 
 // Token statistics of `blocks` full segments (255 spans of 64 cells) of Bernoulli(p_minor) alleles.
@@ -211,6 +216,12 @@ inline FusedTable make_table(double p_minor, const uint64_t* prefix_hist /* [256
         for (int c = 0; c < 256; ++c)
             if (prefix_hist[c]) f[c] += std::max<uint64_t>(1, prefix_hist[c]);
     std::vector<uint8_t> ll = huff_lengths(f, 15);
+    // the kernel fuses [match or separator][allele literal] into one 32-bit token: keep those literals <= 11 bits
+    while (ll['0'] > 11 || ll['1'] > 11 || ll['/'] > 11 || ll['\t'] > 11) {
+        for (uint8_t c : {(uint8_t)'0', (uint8_t)'1', (uint8_t)'/', (uint8_t)'\t'})
+            if (ll[c] > 11) f[c] *= 4;
+        ll = huff_lengths(f, 15);
+    }
     std::vector<uint32_t> lc = huff_codes(ll);
     FusedTable t;
     memset(&t, 0, sizeof t);
