@@ -37,6 +37,7 @@ MALE_ODDS = 0.5
 ROWS_PER_STEP = 8192
 PHILOX_SEED = 0x5EED000000000001
 HOST_SEED = 20260101
+E2E_CHUNK = 320 << 20
 WORKLOAD = ("C2 pop_factory -s 10000 -c 10000 -x 5000000 -f 0.01 -z 2: one step = %d consecutive SNP rows "
             "x 20000 samples (sample -> VCF GT text -> BGZF)" % ROWS_PER_STEP)
 
@@ -267,7 +268,10 @@ def main():
 
     # ------------------------------------------------------------------ end-to-end pass (`e2e`)
     # host buffers in, host buffer out: per step the step's SNP metadata goes H2D, the BGZF bytes come D2H
-    out = np.empty(int(eng.plan(0, R)[1]) + (1 << 20), dtype=np.uint8)
+    # page-locked output buffer: the library DMAs straight into it; smaller passes so that the copy of one pass
+    # overlaps the kernels of the next inside a step
+    out = torch.empty(int(eng.plan(0, R)[1]) + (1 << 20), dtype=torch.uint8, pin_memory=True).numpy()
+    eng.set_chunk_bytes(E2E_CHUNK)
     base = n_steps_total * R
 
     def step_arrays(k):

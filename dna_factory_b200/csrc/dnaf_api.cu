@@ -22,6 +22,7 @@
 #include "k_fused_text.cuh"
 #include "k_sample_format.cuh"
 #include <map>
+#include <unordered_map>
 
 using namespace dnaf;
 
@@ -119,12 +120,23 @@ struct dnaf_ctx {
     DevBuf d_crctab, d_xpow8;
 
     // scratch
-    DevBuf d_plane0, d_plane1, d_text, d_slots, d_sizes, d_crcs, d_offsets, d_totals, d_blocks, d_out, d_geno;
-    PinnedBuf h_out, h_totals, h_blocks;
+    DevBuf d_plane0, d_plane1, d_text, d_slots, d_sizes, d_crcs, d_offsets, d_blocks, d_geno;
+    PinnedBuf h_blocks;
     std::vector<BlockDesc> plan;
 
     cudaEvent_t ev[8] = {};
     cudaStream_t side = nullptr;           // k_fused_text runs here, concurrently with k_fused_auto
+    cudaStream_t copy = nullptr;           // D2H of pass i overlaps the kernels of pass i+1
+    struct OutBuf {                        // what must outlive a pass while the next one runs
+        DevBuf d_out, d_totals;
+        PinnedBuf h_totals, h_out, h_stage;  // h_stage: descriptor uploads of the pass (truly asynchronous H2D)
+        size_t stage_used = 0;
+        cudaEvent_t ev[6] = {};
+        cudaEvent_t ev_totals = nullptr, ev_copied = nullptr;
+        uint32_t nb = 0;
+        uint64_t rows = 0, text = 0;
+        bool gen = false, fused = false, generic_blocks = false;
+    } ob[2];
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool attr_done = false;
 
@@ -140,12 +152,15 @@ struct dnaf_ctx {
     uint64_t gen_text_bytes = 0;
     uint32_t pass_blocks = 0;
     uint32_t fused_threads = 256;
+    int cur_ob = 0;
     std::map<std::pair<uint64_t, uint64_t>, FusedTable> table_cache;
     bool etab_ok = false;
     std::vector<double> bucket_p;          // minor-allele probability per bucket
+    std::unordered_map<uint32_t, int> bucket_of;
+    int bucket_shift = 0;
     std::vector<uint64_t> ph;              // prefix byte model
     uint64_t ph_hash = 0;
-    uint64_t samples_epoch = 0;
+    uint64_t samples_epoch = 0, seg_epoch = ~0ull;
     std::vector<uint64_t> tables_sig;      // what d_ftables currently holds
     std::vector<uint8_t> h_sex;
     DevBuf d_crc4, d_xspan, d_tdesc;
@@ -177,10 +192,10 @@ int fail(dnaf_ctx* c, int code, const char* fmt, ...) {
     } while (0)
 
 template <class T>
-int upload(dnaf_ctx* c, DevBuf& b, const T* src, size_t count) {
+int upload(dnaf_ctx* c, DevBuf& b, const T* src, size_t count, bool sync = true) {
     CU(c, b.reserve(std::max<size_t>(count, 1) * sizeof(T) + 64));
     if (count) CU(c, cudaMemcpyAsync(b.p, src, count * sizeof(T), cudaMemcpyHostToDevice, c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));
+    if (sync) CU(c, cudaStreamSynchronize(c->stream));
     return DNAF_OK;
 }
 
@@ -242,34 +257,36 @@ constexpr int kVariants = 10;  // tables per MAF bucket: auto+prefix, auto, then
 // Called from set_snps: bucket every row by its first threshold, remember which prefix bytes occur.
 int prepare_buckets(dnaf_ctx* c, const uint8_t* kk, const uint32_t* thr, const uint8_t* prefix, const uint64_t* pre_off) {
     c->h_bucket.assign(c->S, 0);
-    c->bucket_p.clear();
-    c->tables_sig.clear();
     if (c->S == 0) return DNAF_OK;
-    // bucket key: the first threshold (minor-allele probability = 1 - (T+1)/2^32), coarsened until <= 512 keys
-    std::map<uint32_t, int> keys;
-    int shift = 0;
-    for (;; shift += 2) {
-        keys.clear();
+    // bucket key: the first threshold (minor-allele probability = 1 - (T+1)/2^32), coarsened (shift) if a
+    // population ever shows more than 512 distinct values.  The key -> bucket map persists across set_snps
+    // calls, so bucket ids -- and with them the uploaded tables -- stay put when successive SNP batches arrive.
+    for (;;) {
         bool ok = true;
-        for (uint64_t r = 0; r < c->S && ok; ++r) {
-            const uint32_t t = kk[r] >= 2 ? thr[r * 4] : 0xFFFFFFFFu;
-            keys.emplace(t >> shift, 0);
-            ok = keys.size() <= 512;
+        uint32_t last_key = 0;
+        int last_bucket = -1;
+        for (uint64_t r = 0; r < c->S; ++r) {
+            const uint32_t key = (kk[r] >= 2 ? thr[r * 4] : 0xFFFFFFFFu) >> c->bucket_shift;
+            if (last_bucket < 0 || key != last_key) {
+                auto it = c->bucket_of.find(key);
+                if (it == c->bucket_of.end()) {
+                    if (c->bucket_of.size() >= 512) { ok = false; break; }
+                    const uint64_t lo = (uint64_t)key << c->bucket_shift;
+                    const uint64_t hi = std::min<uint64_t>(0xFFFFFFFFull, lo + ((1ull << c->bucket_shift) - 1));
+                    const double t_mid = 0.5 * ((double)lo + (double)hi);
+                    c->bucket_p.push_back(std::min(1.0, std::max(0.0, 1.0 - (t_mid + 1.0) / 4294967296.0)));
+                    it = c->bucket_of.emplace(key, (int)c->bucket_of.size()).first;
+                }
+                last_key = key;
+                last_bucket = it->second;
+            }
+            c->h_bucket[r] = (uint16_t)last_bucket;
         }
         if (ok) break;
-    }
-    int nb = 0;
-    for (auto& kv : keys) kv.second = nb++;
-    c->bucket_p.resize(nb);
-    for (auto& kv : keys) {
-        const uint64_t lo = (uint64_t)kv.first << shift;
-        const uint64_t hi = std::min<uint64_t>(0xFFFFFFFFull, lo + ((1ull << shift) - 1));
-        const double t_mid = 0.5 * ((double)lo + (double)hi);
-        c->bucket_p[kv.second] = std::min(1.0, std::max(0.0, 1.0 - (t_mid + 1.0) / 4294967296.0));
-    }
-    for (uint64_t r = 0; r < c->S; ++r) {
-        const uint32_t t = kk[r] >= 2 ? thr[r * 4] : 0xFFFFFFFFu;
-        c->h_bucket[r] = (uint16_t)keys[t >> shift];
+        c->bucket_shift += 2;  // too many distinct thresholds: merge neighbours and start over
+        c->bucket_of.clear();
+        c->bucket_p.clear();
+        c->tables_sig.clear();
     }
     // prefix byte model (x16 fixed point per row): which bytes occur, weighted by kind -- deliberately not the
     // exact counts, so that tables can be cached across set_snps calls with similar prefixes
@@ -376,6 +393,8 @@ int ensure_tables(dnaf_ctx* c) {
 // Segments of an autosome row (balanced, at most 254 spans of 64 samples each) and the linear CRC of their
 // all-reference template bodies.
 void build_segments(dnaf_ctx* c) {
+    if (c->seg_epoch == c->samples_epoch) return;  // depends on the sample set only
+    c->seg_epoch = c->samples_epoch;
     c->h_seg_cell0.clear();
     c->h_seg_crc.clear();
     c->fused_threads = 64;
@@ -542,6 +561,7 @@ struct Sink {
     uint8_t* buf = nullptr;  // host buffer mode
     uint64_t cap = 0, used = 0;
     bool device_only = false;
+    bool pinned = false;     // buf is page-locked host memory
 };
 
 int deliver(dnaf_ctx* c, Sink& s, const uint8_t* data, uint64_t n) {
@@ -556,21 +576,45 @@ int deliver(dnaf_ctx* c, Sink& s, const uint8_t* data, uint64_t n) {
     return DNAF_OK;
 }
 
+// Uploads a host vector through the pass's page-locked staging arena, so the copy is asynchronous and the
+// host can go on planning while the previous pass still runs.  reserve_stage() sizes the arena up front.
 template <class T>
 int upload_async(dnaf_ctx* c, DevBuf& b, const std::vector<T>& v) {
     CU(c, b.reserve(std::max<size_t>(v.size(), 1) * sizeof(T)));
-    if (!v.empty()) CU(c, cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    if (v.empty()) return DNAF_OK;
+    dnaf_ctx::OutBuf& B = c->ob[c->cur_ob];
+    const size_t bytes = v.size() * sizeof(T);
+    const size_t at = (B.stage_used + 63) & ~size_t(63);
+    if (at + bytes > B.h_stage.cap) {  // not planned for: fall back to a pageable (synchronising) copy
+        CU(c, cudaMemcpyAsync(b.p, v.data(), bytes, cudaMemcpyHostToDevice, c->stream));
+        return DNAF_OK;
+    }
+    memcpy(B.h_stage.as<uint8_t>() + at, v.data(), bytes);
+    B.stage_used = at + bytes;
+    CU(c, cudaMemcpyAsync(b.p, B.h_stage.as<uint8_t>() + at, bytes, cudaMemcpyHostToDevice, c->stream));
     return DNAF_OK;
 }
 
-int reserve_outputs(dnaf_ctx* c, uint32_t nb) {
+int reserve_stage(dnaf_ctx* c, dnaf_ctx::OutBuf& B) {
+    const size_t need = c->fplan.size() * sizeof(FusedDesc) + c->tplan.size() * sizeof(TextDesc) +
+                        c->plan.size() * sizeof(BlockDesc) + (c->gslot.size() + c->grow.size() + c->olocal.size() +
+                        c->osub.size()) * 4 + c->goff.size() * 8 + 1024;
+    if (need > B.h_stage.cap) {
+        CU(c, cudaEventSynchronize(B.ev[5]));  // the arena may still feed the previous use of this buffer
+        CU(c, B.h_stage.reserve(need * 2));
+    }
+    B.stage_used = 0;
+    return DNAF_OK;
+}
+
+int reserve_outputs(dnaf_ctx* c, dnaf_ctx::OutBuf& B, uint32_t nb) {
     CU(c, c->d_slots.reserve((size_t)nb * kSlot));
     CU(c, c->d_sizes.reserve(nb * sizeof(uint32_t)));
     CU(c, c->d_crcs.reserve(nb * sizeof(uint32_t)));
     CU(c, c->d_offsets.reserve(nb * sizeof(uint64_t)));
-    CU(c, c->d_totals.reserve(2 * sizeof(uint64_t)));
-    CU(c, c->d_out.reserve((size_t)nb * kSlot));
-    CU(c, c->h_totals.reserve(2 * sizeof(uint64_t)));
+    CU(c, B.d_totals.reserve(2 * sizeof(uint64_t)));
+    CU(c, B.d_out.reserve((size_t)nb * kSlot));
+    CU(c, B.h_totals.reserve(2 * sizeof(uint64_t)));
     if (!c->attr_done) {
         CU(c, cudaFuncSetAttribute(k_bgzf_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DeflateSmem)));
         c->attr_done = true;
@@ -594,32 +638,77 @@ int launch_generic(dnaf_ctx* c, dnaf_stats* st) {
     return DNAF_OK;
 }
 
-// scan + compact the first nb slots, then hand the bytes to the sink
-int finish_pass(dnaf_ctx* c, uint32_t nb, Sink& sink, dnaf_stats* st) {
-    if (!nb) return DNAF_OK;
-    k_scan_sizes<<<1, 1024, 0, c->stream>>>(c->d_sizes.as<uint32_t>(), nb, c->d_offsets.as<uint64_t>(),
-                                            c->d_crcs.as<uint32_t>(), c->d_totals.as<uint64_t>());
-    k_compact<<<nb, 256, 0, c->stream>>>(c->d_slots.as<uint8_t>(), kSlot, c->d_sizes.as<uint32_t>(),
-                                         c->d_offsets.as<uint64_t>(), c->d_out.as<uint8_t>());
-    CU(c, cudaEventRecord(c->ev[5], c->stream));
+// scan + compact the first nb slots into B.d_out; the totals follow on the copy stream
+int close_pass(dnaf_ctx* c, dnaf_ctx::OutBuf& B, uint32_t nb, dnaf_stats* st) {
+    B.nb = nb;
+    if (nb) {
+        k_scan_sizes<<<1, 1024, 0, c->stream>>>(c->d_sizes.as<uint32_t>(), nb, c->d_offsets.as<uint64_t>(),
+                                                c->d_crcs.as<uint32_t>(), B.d_totals.as<uint64_t>());
+        k_compact<<<nb, 256, 0, c->stream>>>(c->d_slots.as<uint8_t>(), kSlot, c->d_sizes.as<uint32_t>(),
+                                             c->d_offsets.as<uint64_t>(), B.d_out.as<uint8_t>());
+        if (st) st->kernel_launches += 2;
+    }
+    CU(c, cudaEventRecord(B.ev[5], c->stream));
     CU(c, cudaGetLastError());
-    CU(c, cudaMemcpyAsync(c->h_totals.p, c->d_totals.p, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));
-    const uint64_t bytes = c->h_totals.as<uint64_t>()[0];
+    return DNAF_OK;
+}
+
+// Queue the 16-byte totals read-back of a closed pass on the copy stream.  Called AFTER the previous pass
+// has been retired: the copy stream is FIFO, so queuing this wait-for-kernels first would hold that
+// pass's data copy back until the new kernels are done.
+int queue_totals(dnaf_ctx* c, dnaf_ctx::OutBuf& B) {
+    if (B.nb) {
+        CU(c, cudaStreamWaitEvent(c->copy, B.ev[5], 0));
+        CU(c, cudaMemcpyAsync(B.h_totals.p, B.d_totals.p, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->copy));
+    }
+    CU(c, cudaEventRecord(B.ev_totals, c->copy));
+    return DNAF_OK;
+}
+
+// wait for a closed pass, move its bytes to the sink (directly into a pinned caller buffer when possible)
+int retire_pass(dnaf_ctx* c, dnaf_ctx::OutBuf& B, Sink& sink, dnaf_stats* st) {
+    CU(c, cudaEventSynchronize(B.ev[5]));
+    CU(c, cudaEventSynchronize(B.ev_totals));
+    const uint64_t bytes = B.nb ? B.h_totals.as<uint64_t>()[0] : 0;
     if (st) {
         st->bgzf_bytes += bytes;
-        st->bgzf_blocks += nb;
-        st->crc_xor ^= (uint32_t)c->h_totals.as<uint64_t>()[1];
-        st->kernel_launches += 2;
+        st->bgzf_blocks += B.nb;
+        if (B.nb) st->crc_xor ^= (uint32_t)B.h_totals.as<uint64_t>()[1];
+        float t01 = 0, t12 = 0, t23 = 0, t34 = 0, t45 = 0, t05 = 0;
+        cudaEventElapsedTime(&t01, B.ev[0], B.ev[1]);
+        cudaEventElapsedTime(&t12, B.ev[1], B.ev[2]);
+        cudaEventElapsedTime(&t23, B.ev[2], B.ev[3]);
+        cudaEventElapsedTime(&t34, B.ev[3], B.ev[4]);
+        cudaEventElapsedTime(&t45, B.ev[4], B.ev[5]);
+        cudaEventElapsedTime(&t05, B.ev[0], B.ev[5]);
+        if (B.gen) {
+            st->ms_sample += t01;
+            st->ms_format += t12;
+        }
+        st->ms_deflate += (B.generic_blocks ? t23 : 0.f) + t45;
+        if (B.fused) st->ms_fused += t34;
+        st->ms_total += t05;
+        st->rows += B.rows;
+        st->text_bytes += B.text;
     }
-    if (!sink.device_only) {
-        CU(c, c->h_out.reserve(bytes));
-        CU(c, cudaMemcpyAsync(c->h_out.p, c->d_out.p, bytes, cudaMemcpyDeviceToHost, c->stream));
-        CU(c, cudaStreamSynchronize(c->stream));
-        return deliver(c, sink, c->h_out.as<uint8_t>(), bytes);
+    if (sink.device_only || !bytes) {
+        sink.used += bytes;
+        return DNAF_OK;
     }
-    sink.used += bytes;
-    return DNAF_OK;
+    if (sink.buf && sink.pinned) {  // no staging copy: DMA straight into the caller's page-locked buffer
+        if (sink.used + bytes > sink.cap)
+            return fail(c, DNAF_E_SPACE, "output buffer too small: need more than %llu bytes", (unsigned long long)sink.cap);
+        CU(c, cudaMemcpyAsync(sink.buf + sink.used, B.d_out.p, bytes, cudaMemcpyDeviceToHost, c->copy));
+        CU(c, cudaEventRecord(B.ev_copied, c->copy));
+        CU(c, cudaEventSynchronize(B.ev_copied));
+        sink.used += bytes;
+        return DNAF_OK;
+    }
+    CU(c, B.h_out.reserve(bytes));
+    CU(c, cudaMemcpyAsync(B.h_out.p, B.d_out.p, bytes, cudaMemcpyDeviceToHost, c->copy));
+    CU(c, cudaEventRecord(B.ev_copied, c->copy));
+    CU(c, cudaEventSynchronize(B.ev_copied));
+    return deliver(c, sink, B.h_out.as<uint8_t>(), bytes);
 }
 
 // sample (+ overrides) `rows` rows into the plane buffers; row list optional (d_grow), overrides as local pairs
@@ -698,13 +787,22 @@ int generate_impl(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t se
     CU(c, cudaSetDevice(c->dev));
     dnaf_stats local;
     memset(&local, 0, sizeof local);
+    if (sink.buf) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, sink.buf) == cudaSuccess) sink.pinned = attr.type == cudaMemoryTypeHost;
+        else cudaGetLastError();
+    }
     uint64_t r0 = row_begin;
+    int cur = 0, pending = -1;
     while (r0 < row_end) {
         const uint64_t r1 = next_chunk_end(c, r0, row_end, c->chunk_bytes);
+        dnaf_ctx::OutBuf& B = c->ob[cur];
         plan_pass(c, r0, r1, c->h_k.data());
-        rc = reserve_outputs(c, c->pass_blocks);
+        c->cur_ob = cur;
+        rc = reserve_outputs(c, B, c->pass_blocks);
+        if (!rc) rc = reserve_stage(c, B);
         if (rc) return rc;
-        CU(c, cudaEventRecord(c->ev[0], c->stream));
+        CU(c, cudaEventRecord(B.ev[0], c->stream));
         const uint32_t grows = (uint32_t)c->grow.size();
         if (grows) {
             rc = upload_async(c, c->d_grow, c->grow);
@@ -714,15 +812,15 @@ int generate_impl(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t se
                                      c->d_olocal.as<uint32_t>(), c->d_osub.as<uint32_t>(), &local);
             if (rc) return rc;
         }
-        CU(c, cudaEventRecord(c->ev[1], c->stream));
+        CU(c, cudaEventRecord(B.ev[1], c->stream));
         if (grows) {
             rc = run_format(c, r0, grows, c->d_grow.as<uint32_t>(), c->d_goff.as<uint64_t>(), c->gen_text_bytes, &local);
             if (rc) return rc;
         }
-        CU(c, cudaEventRecord(c->ev[2], c->stream));
+        CU(c, cudaEventRecord(B.ev[2], c->stream));
         rc = launch_generic(c, &local);
         if (rc) return rc;
-        CU(c, cudaEventRecord(c->ev[3], c->stream));
+        CU(c, cudaEventRecord(B.ev[3], c->stream));
         if (!c->tplan.empty()) {
             rc = upload_async(c, c->d_tdesc, c->tplan);
             if (rc) return rc;
@@ -777,26 +875,28 @@ int generate_impl(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t se
             CU(c, cudaGetLastError());
         }
         if (!c->tplan.empty()) CU(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
-        CU(c, cudaEventRecord(c->ev[4], c->stream));
-        rc = finish_pass(c, c->pass_blocks, sink, &local);
+        CU(c, cudaEventRecord(B.ev[4], c->stream));
+        B.rows = r1 - r0;
+        B.text = c->h_row_off[r1] - c->h_row_off[r0];
+        B.gen = grows != 0;
+        B.generic_blocks = !c->plan.empty();
+        B.fused = !c->fplan.empty() || !c->tplan.empty();
+        rc = close_pass(c, B, c->pass_blocks, &local);
         if (rc) return rc;
-        float t01 = 0, t12 = 0, t23 = 0, t34 = 0, t45 = 0, t05 = 0;
-        cudaEventElapsedTime(&t01, c->ev[0], c->ev[1]);
-        cudaEventElapsedTime(&t12, c->ev[1], c->ev[2]);
-        cudaEventElapsedTime(&t23, c->ev[2], c->ev[3]);
-        cudaEventElapsedTime(&t34, c->ev[3], c->ev[4]);
-        cudaEventElapsedTime(&t45, c->ev[4], c->ev[5]);
-        cudaEventElapsedTime(&t05, c->ev[0], c->ev[5]);
-        if (grows) {
-            local.ms_sample += t01;
-            local.ms_format += t12;
+        // the previous pass is copied out while this one computes
+        if (pending >= 0) {
+            rc = retire_pass(c, c->ob[pending], sink, &local);
+            if (rc) return rc;
         }
-        local.ms_deflate += (c->plan.empty() ? 0.f : t23) + t45;
-        if (!c->fplan.empty() || !c->tplan.empty()) local.ms_fused += t34;
-        local.ms_total += t05;
-        local.rows += r1 - r0;
-        local.text_bytes += c->h_row_off[r1] - c->h_row_off[r0];
+        rc = queue_totals(c, B);
+        if (rc) return rc;
+        pending = cur;
+        cur ^= 1;
         r0 = r1;
+    }
+    if (pending >= 0) {
+        rc = retire_pass(c, c->ob[pending], sink, &local);
+        if (rc) return rc;
     }
     local.calls = local.rows * c->n;
     if (st) *st = local;
@@ -838,6 +938,13 @@ int dnaf_create(int device_ordinal, dnaf_ctx** out) {
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
         if ((e = cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, hi)) != cudaSuccess) return bail("cudaStreamCreate", e);
     }
+    if ((e = cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    for (auto& b : c->ob) {
+        for (auto& ev : b.ev)
+            if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
+        if ((e = cudaEventCreateWithFlags(&b.ev_totals, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+        if ((e = cudaEventCreateWithFlags(&b.ev_copied, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    }
     if ((e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     // CRC tables: byte table and x^(8k) mod P for k = 0..kBlk
@@ -867,6 +974,13 @@ void dnaf_destroy(dnaf_ctx* c) {
     for (auto& ev : c->ev)
         if (ev) cudaEventDestroy(ev);
     if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
+    if (c->copy) { cudaStreamSynchronize(c->copy); cudaStreamDestroy(c->copy); }
+    for (auto& b : c->ob) {
+        for (auto& ev : b.ev)
+            if (ev) cudaEventDestroy(ev);
+        if (b.ev_totals) cudaEventDestroy(b.ev_totals);
+        if (b.ev_copied) cudaEventDestroy(b.ev_copied);
+    }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -969,10 +1083,11 @@ int dnaf_set_snps(dnaf_ctx* c, uint64_t S, const uint8_t* cls, const uint8_t* k,
     c->h_k.assign(k, k + S);
     c->h_plen.resize(S);
     for (uint64_t r = 0; r < S; ++r) c->h_plen[r] = (uint32_t)(pre_off[r + 1] - pre_off[r]);
-    int rc = upload(c, c->d_cls, cls, S);
-    if (!rc) rc = upload(c, c->d_k, k, S);
-    if (!rc) rc = upload(c, c->d_thr, thr, S * 4);
-    if (!rc) rc = upload(c, c->d_prefix, prefix, S ? pre_off[S] : 0);
+    // pageable sources: each copy returns once the data is staged, one synchronise covers them all
+    int rc = upload(c, c->d_cls, cls, S, false);
+    if (!rc) rc = upload(c, c->d_k, k, S, false);
+    if (!rc) rc = upload(c, c->d_thr, thr, S * 4, false);
+    if (!rc) rc = upload(c, c->d_prefix, prefix, S ? pre_off[S] : 0, false);
     if (!rc) rc = upload(c, c->d_pre_off, pre_off, S + 1);
     if (rc) return rc;
     if (S == 0) {
@@ -1139,15 +1254,22 @@ int dnaf_bgzf_compress(dnaf_ctx* c, const uint8_t* text, uint64_t n, int level, 
         c->gslot.clear();
         for (uint64_t o = 0; o < piece; o += kBlk)
             c->plan.push_back({o, (uint32_t)std::min<uint64_t>(kBlk, piece - o), 0});
-        int rc = reserve_outputs(c, (uint32_t)c->plan.size());
+        dnaf_ctx::OutBuf& B = c->ob[0];
+        c->cur_ob = 0;
+        int rc = reserve_outputs(c, B, (uint32_t)c->plan.size());
+        if (!rc) rc = reserve_stage(c, B);
         if (rc) return rc;
-        CU(c, cudaEventRecord(c->ev[0], c->stream));
+        for (int e = 0; e < 5; ++e) CU(c, cudaEventRecord(B.ev[e], c->stream));
+        B.rows = 0;
+        B.text = 0;
+        B.gen = false;
+        B.fused = false;
+        B.generic_blocks = true;
         rc = launch_generic(c, &local);
-        if (!rc) rc = finish_pass(c, (uint32_t)c->plan.size(), s, &local);
+        if (!rc) rc = close_pass(c, B, (uint32_t)c->plan.size(), &local);
+        if (!rc) rc = queue_totals(c, B);
+        if (!rc) rc = retire_pass(c, B, s, &local);
         if (rc) return rc;
-        float ms = 0;
-        cudaEventElapsedTime(&ms, c->ev[0], c->ev[5]);
-        local.ms_deflate += ms;
         local.text_bytes += piece;
         done += piece;
     }
