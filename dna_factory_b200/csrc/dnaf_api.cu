@@ -20,6 +20,7 @@
 #include "k_deflate.cuh"
 #include "k_fused.cuh"
 #include "k_fused_text.cuh"
+#include "k_fused_x.cuh"
 #include "k_sample_format.cuh"
 #include <map>
 #include <unordered_map>
@@ -163,7 +164,11 @@ struct dnaf_ctx {
     uint64_t samples_epoch = 0, seg_epoch = ~0ull;
     std::vector<uint64_t> tables_sig;      // what d_ftables currently holds
     std::vector<uint8_t> h_sex;
-    DevBuf d_crc4, d_xspan, d_tdesc;
+    DevBuf d_crc4, d_xspan, d_tdesc, d_xspans, d_xdesc;
+    std::vector<XSpan> h_xspans;
+    std::vector<uint32_t> h_seg_crc_x;     // L(template body) per X segment
+    std::vector<uint32_t> h_xoff;
+    std::vector<FusedDesc> xplan;
     std::vector<TextDesc> tplan;
     std::vector<uint32_t> seg_byte0[4];    // k_fused_text segments per chromosome class (+ end sentinel)
     uint32_t text_threads = 64;
@@ -252,7 +257,7 @@ uint32_t raw_crc(const uint8_t* p, size_t n, const uint32_t* tab) {
     return c;
 }
 
-constexpr int kVariants = 10;  // tables per MAF bucket: auto+prefix, auto, then (class x {prefix, no prefix}) for k_fused_text
+constexpr int kVariants = 12;  // tables per MAF bucket: auto+prefix, auto, (class x {prefix, no prefix}) for k_fused_text, X+prefix, X for k_fused_x
 
 // Called from set_snps: bucket every row by its first threshold, remember which prefix bytes occur.
 int prepare_buckets(dnaf_ctx* c, const uint8_t* kk, const uint32_t* thr, const uint8_t* prefix, const uint64_t* pre_off) {
@@ -311,6 +316,8 @@ int ensure_tables(dnaf_ctx* c) {
         const int b = c->h_bucket[r];
         if (c->h_cls[r] == kAuto && c->h_k[r] <= 2) {
             need[b * kVariants + 0] = need[b * kVariants + 1] = 1;
+        } else if (c->h_cls[r] == kX && c->h_k[r] <= 2) {
+            need[b * kVariants + 10] = need[b * kVariants + 11] = 1;
         } else {
             need[b * kVariants + 2 + 2 * c->h_cls[r]] = need[b * kVariants + 3 + 2 * c->h_cls[r]] = 1;
         }
@@ -334,15 +341,18 @@ int ensure_tables(dnaf_ctx* c) {
             for (int v = 0; v < kVariants; ++v) {
                 if (!need[b * kVariants + v]) continue;
                 const bool with_prefix = (v & 1) == 0;
-                const int cls = v < 2 ? -1 : (v - 2) / 2;
+                const int cls = v < 2 ? -1 : (v >= 10 ? 100 : (v - 2) / 2);   // -1: autosome cells, 100: X cells
                 const uint64_t vkey = (with_prefix ? c->ph_hash : 0x5bd1e995ull) * 31 + (uint64_t)(cls + 1) * 1000003ull +
                                       (cls >= 0 ? c->samples_epoch * 0x9E3779B97F4A7C15ull : 0);
                 auto key = std::make_pair(pbits, vkey);
                 auto it = c->table_cache.find(key);
                 if (it == c->table_cache.end()) {
                     const uint64_t* hist = with_prefix ? c->ph.data() : nullptr;
+                    const int per_block = (int)std::max<size_t>(1, c->h_seg_cell0.size() > 1
+                                                                       ? (c->h_seg_cell0[1] - c->h_seg_cell0[0] + 63) / 64 : 1);
                     FusedTable t = cls < 0 ? hosttab::make_table(p, hist)
-                                           : hosttab::make_text_table(cls, p, c->h_sex.data(), c->n, hist);
+                                   : cls == 100 ? hosttab::make_table_x(p, c->h_xspans, per_block, hist)
+                                                : hosttab::make_text_table(cls, p, c->h_sex.data(), c->n, hist);
                     if (t.hdr_bits == 0xFFFFFFFFu) return DNAF_OK;  // header too long: stay on the generic path
                     it = c->table_cache.emplace(key, t).first;
                 }
@@ -421,6 +431,20 @@ void build_segments(dnaf_ctx* c) {
     }
     c->h_seg_cell0.push_back(c->n);
     c->fused_threads = std::max(64u, (per + 31u) / 32u * 32u);
+    {   // X rows use the same sample segments; their template is the all-reference X body
+        std::vector<uint8_t> xbody;
+        xbody.reserve(c->body[kX]);
+        for (uint32_t i = 0; i < c->n; ++i) {
+            xbody.push_back('0');
+            if (c->h_sex[i] != 1) { xbody.push_back('/'); xbody.push_back('0'); }
+            xbody.push_back(i + 1 == c->n ? '\n' : '\t');
+        }
+        c->h_seg_crc_x.clear();
+        for (size_t sg = 0; sg + 1 < c->h_seg_cell0.size(); ++sg) {
+            const uint32_t b0 = c->h_xoff[c->h_seg_cell0[sg]], b1 = c->h_xoff[c->h_seg_cell0[sg + 1]];
+            c->h_seg_crc_x.push_back(raw_crc(xbody.data() + b0, b1 - b0, tab.data()));
+        }
+    }
     // k_fused_text: balanced byte segments (multiples of 256 bytes) of every class body
     c->text_threads = 64;
     for (int cls = 0; cls < 4; ++cls) {
@@ -436,17 +460,20 @@ void build_segments(dnaf_ctx* c) {
     }
 }
 
-// 0 = generic three-kernel path, 1 = k_fused_auto, 2 = k_fused_text
+// 0 = generic three-kernel path, 1 = k_fused_auto, 2 = k_fused_text, 3 = k_fused_x
 inline int row_kind(const dnaf_ctx* c, uint64_t r, const uint8_t* hk) {
     if (!c->fused || !c->fused_ok || c->h_plen[r] < 1 || c->h_plen[r] > 64 || c->n == 0) return 0;
     if (c->body[c->h_cls[r]] < kFusedMinRowBytes) return 0;
-    return (c->h_cls[r] == kAuto && hk[r] <= 2) ? 1 : 2;
+    if (hk[r] <= 2 && c->h_cls[r] == kAuto) return 1;
+    if (hk[r] <= 2 && c->h_cls[r] == kX) return 3;
+    return 2;
 }
 inline bool row_is_fused(const dnaf_ctx* c, uint64_t r, const uint8_t* hk) { return row_kind(c, r, hk) != 0; }
 
 // BGZF block plan of one pass (rows [r0,r1)): fused segments and generic blocks, slots in row order.
 void plan_pass(dnaf_ctx* c, uint64_t r0, uint64_t r1, const uint8_t* hk) {
     c->fplan.clear();
+    c->xplan.clear();
     c->tplan.clear();
     c->plan.clear();
     c->gslot.clear();
@@ -483,7 +510,7 @@ void plan_pass(dnaf_ctx* c, uint64_t r0, uint64_t r1, const uint8_t* hk) {
             ++r;
             continue;
         }
-        if (kind == 1) {
+        if (kind == 1 || kind == 3) {
             size_t oe = o;
             while (oe < c->h_orow.size() && c->h_orow[oe] == r) ++oe;
             const size_t nseg = c->h_seg_crc.size();
@@ -496,9 +523,15 @@ void plan_pass(dnaf_ctx* c, uint64_t r0, uint64_t r1, const uint8_t* hk) {
                 d.flags = (sgi == 0 ? 1u : 0u) | (sgi + 1 == nseg ? 2u : 0u);
                 d.ovr_first = (uint32_t)o;
                 d.ovr_count = (uint32_t)(oe - o);
-                d.table = (uint32_t)c->h_bucket[r] * kVariants + (sgi == 0 ? 0u : 1u);
-                d.body_crc = c->h_seg_crc[sgi];
-                c->fplan.push_back(d);
+                if (kind == 1) {
+                    d.table = (uint32_t)c->h_bucket[r] * kVariants + (sgi == 0 ? 0u : 1u);
+                    d.body_crc = c->h_seg_crc[sgi];
+                    c->fplan.push_back(d);
+                } else {
+                    d.table = (uint32_t)c->h_bucket[r] * kVariants + 10u + (sgi == 0 ? 0u : 1u);
+                    d.body_crc = c->h_seg_crc_x[sgi];
+                    c->xplan.push_back(d);
+                }
             }
             o = oe;
             ++r;
@@ -596,7 +629,7 @@ int upload_async(dnaf_ctx* c, DevBuf& b, const std::vector<T>& v) {
 }
 
 int reserve_stage(dnaf_ctx* c, dnaf_ctx::OutBuf& B) {
-    const size_t need = c->fplan.size() * sizeof(FusedDesc) + c->tplan.size() * sizeof(TextDesc) +
+    const size_t need = (c->fplan.size() + c->xplan.size()) * sizeof(FusedDesc) + c->tplan.size() * sizeof(TextDesc) +
                         c->plan.size() * sizeof(BlockDesc) + (c->gslot.size() + c->grow.size() + c->olocal.size() +
                         c->osub.size()) * 4 + c->goff.size() * 8 + 1024;
     if (need > B.h_stage.cap) {
@@ -874,13 +907,37 @@ int generate_impl(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t se
             local.kernel_launches += 1;
             CU(c, cudaGetLastError());
         }
+        if (!c->xplan.empty()) {
+            rc = upload_async(c, c->d_xdesc, c->xplan);
+            if (rc) return rc;
+            XArgs xa;
+            xa.f.sv = sample_view(c);
+            xa.f.nv = snp_view(c);
+            xa.f.desc = c->d_xdesc.as<FusedDesc>();
+            xa.f.tables = c->d_ftables.as<FusedTable>();
+            xa.f.etab = c->d_etab.as<uint32_t>();
+            xa.f.crctab = c->d_crctab.as<uint32_t>();
+            xa.f.xpow8 = c->d_xpow8.as<uint32_t>();
+            xa.f.orow = c->d_orow.as<uint64_t>();
+            xa.f.osamp = c->d_osamp.as<uint32_t>();
+            xa.f.row_base = c->row_base;
+            xa.f.k0 = (uint32_t)seed;
+            xa.f.k1 = (uint32_t)(seed >> 32);
+            xa.f.slots = c->d_slots.as<uint8_t>();
+            xa.f.sizes = c->d_sizes.as<uint32_t>();
+            xa.f.crcs = c->d_crcs.as<uint32_t>();
+            xa.xspans = c->d_xspans.as<XSpan>();
+            k_fused_x<<<(uint32_t)c->xplan.size(), c->fused_threads, 0, c->stream>>>(xa);
+            local.kernel_launches += 1;
+            CU(c, cudaGetLastError());
+        }
         if (!c->tplan.empty()) CU(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
         CU(c, cudaEventRecord(B.ev[4], c->stream));
         B.rows = r1 - r0;
         B.text = c->h_row_off[r1] - c->h_row_off[r0];
         B.gen = grows != 0;
         B.generic_blocks = !c->plan.empty();
-        B.fused = !c->fplan.empty() || !c->tplan.empty();
+        B.fused = !c->fplan.empty() || !c->tplan.empty() || !c->xplan.empty();
         rc = close_pass(c, B, c->pass_blocks, &local);
         if (rc) return rc;
         // the previous pass is copied out while this one computes
@@ -1042,7 +1099,11 @@ int dnaf_set_samples(dnaf_ctx* c, uint32_t n, const uint8_t* sex, const uint8_t*
     if (!rc) rc = upload(c, c->d_xoff, xoff.data(), xoff.size());
     if (rc) return rc;
     c->h_sex.assign(sex, sex + n);
+    c->h_xoff = xoff;
     c->samples_epoch++;
+    c->h_xspans = hosttab::build_xspans(sex, n, xoff.data());
+    rc = upload(c, c->d_xspans, c->h_xspans.data(), c->h_xspans.size());
+    if (rc) return rc;
     {   // X rows: the sample that holds body byte 256*k (for k_fused_text)
         std::vector<uint32_t> xspan((size_t)acc / 256 + 2, 0);
         uint32_t i = 0;

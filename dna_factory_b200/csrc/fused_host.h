@@ -14,6 +14,7 @@
 
 #include "k_fused.cuh"
 #include "k_fused_text.cuh"
+#include "k_fused_x.cuh"
 
 namespace dnaf {
 namespace hosttab {
@@ -175,6 +176,10 @@ struct HistSink {
         else if (gap) match(gap);
         lit(bit);
     }
+    void gap_tok(int gap, int id) {
+        if (gap) match(gap);
+        lit(id);
+    }
 };
 
 // Token statistics of `blocks` full segments (255 spans of 64 cells) of Bernoulli(p_minor) alleles.
@@ -202,21 +207,20 @@ inline HistSink simulate(double p_minor, int blocks) {
     return h;
 }
 
-// One table: codes for cell literals, all match lengths, EOB (+ prefix byte literals when `prefix_hist`).
-inline FusedTable make_table(double p_minor, const uint64_t* prefix_hist /* [256] per-row average x 16, or null */) {
-    const int kBlocks = 4;
-    HistSink h = simulate(p_minor, kBlocks);
+// Codes for cell literals, all match lengths, EOB (+ prefix byte literals when `prefix_hist`) from token counts
+// gathered over `blocks` blocks.
+inline FusedTable finish_cell_table(const HistSink& h, uint64_t blocks, const uint64_t* prefix_hist) {
     std::vector<uint64_t> f(286, 0);
     const uint8_t lit_byte[5] = {'0', '1', '/', '\t', '\n'};
     const uint64_t scale = 16;  // fixed-point so that per-row prefix averages below one occurrence still count
-    for (int i = 0; i < 5; ++i) f[lit_byte[i]] += (h.nlit[i] * scale) / kBlocks + 1;
-    for (int i = 0; i < 29; ++i) f[257 + i] += (h.nlen[i] * scale) / kBlocks + 1;
+    for (int i = 0; i < 5; ++i) f[lit_byte[i]] += (h.nlit[i] * scale) / blocks + 1;
+    for (int i = 0; i < 29; ++i) f[257 + i] += (h.nlen[i] * scale) / blocks + 1;
     f[256] = scale;
     if (prefix_hist)
         for (int c = 0; c < 256; ++c)
             if (prefix_hist[c]) f[c] += std::max<uint64_t>(1, prefix_hist[c]);
     std::vector<uint8_t> ll = huff_lengths(f, 15);
-    // the kernel fuses [match or separator][allele literal] into one 32-bit token: keep those literals <= 11 bits
+    // the kernels fuse [match or separator][literal] into one 32-bit token: keep the cell literals <= 11 bits
     while (ll['0'] > 11 || ll['1'] > 11 || ll['/'] > 11 || ll['\t'] > 11) {
         for (uint8_t c : {(uint8_t)'0', (uint8_t)'1', (uint8_t)'/', (uint8_t)'\t'})
             if (ll[c] > 11) f[c] *= 4;
@@ -241,6 +245,97 @@ inline FusedTable make_table(double p_minor, const uint64_t* prefix_hist /* [256
     return t;
 }
 
+inline FusedTable make_table(double p_minor, const uint64_t* prefix_hist) {
+    const int kBlocks = 4;
+    return finish_cell_table(simulate(p_minor, kBlocks), kBlocks, prefix_hist);
+}
+
+// Static per-population description of the X-row spans (k_fused_x.cuh): compaction masks (Hacker's Delight
+// 7-4 "compress", move masks precomputed), separator kinds and separator mismatches.
+inline std::vector<XSpan> build_xspans(const uint8_t* sex, uint32_t n, const uint32_t* xoff) {
+    const uint32_t nspans = (n + 63u) / 64u;
+    std::vector<XSpan> out(nspans);
+    // separator kinds over the whole row, in compacted-allele order
+    std::vector<uint8_t> kinds;
+    kinds.reserve((size_t)2 * n);
+    for (uint32_t i = 0; i < n; ++i) {
+        if (sex[i] == 1) kinds.push_back(0);             // "a\t"
+        else { kinds.push_back(1); kinds.push_back(0); } // "a/b\t"
+    }
+    size_t k0 = 0;
+    for (uint32_t sp = 0; sp < nspans; ++sp) {
+        XSpan xs;
+        memset(&xs, 0, sizeof xs);
+        const uint32_t i0 = 64u * sp, i1 = std::min(n, i0 + 64u);
+        for (uint32_t i = i0; i < i1; ++i) {
+            const uint32_t j = 2u * (i - i0);
+            xs.used[j >> 5] |= 1u << (j & 31u);
+            if (sex[i] != 1) xs.used[(j + 1) >> 5] |= 1u << ((j + 1) & 31u);
+        }
+        uint32_t L = 0;
+        for (int w = 0; w < 4; ++w) {
+            uint32_t m = xs.used[w];
+            xs.len[w] = (uint32_t)__builtin_popcount(m);
+            uint32_t mk = ~m << 1;
+            for (int i = 0; i < 5; ++i) {
+                uint32_t mp = mk ^ (mk << 1);
+                mp ^= mp << 2;
+                mp ^= mp << 4;
+                mp ^= mp << 8;
+                mp ^= mp << 16;
+                const uint32_t mv = mp & m;
+                xs.mv[w][i] = mv;
+                m = (m ^ mv) | (mv >> (1 << i));
+                mk &= ~mp;
+            }
+            L += xs.len[w];
+        }
+        for (uint32_t k = 0; k < L; ++k) {
+            const size_t K = k0 + k;
+            if (kinds[K]) xs.sk[k >> 5] |= 1u << (k & 31u);
+            if (K < 2 || kinds[K] != kinds[K - 2]) xs.sm[k >> 5] |= 1u << (k & 31u);
+        }
+        xs.byte_off = xoff[i0];
+        out[sp] = xs;
+        k0 += L;
+    }
+    return out;
+}
+
+// Table for k_fused_x: token statistics of X rows with Bernoulli(p_minor) alleles over the real spans.
+inline HistSink simulate_x(double p_minor, const std::vector<XSpan>& xspans, int per_block) {
+    HistSink h;
+    uint64_t st = 0xA24BAED4963EE407ull ^ (uint64_t)(p_minor * 1e9);
+    auto next = [&]() {
+        st ^= st << 13; st ^= st >> 7; st ^= st << 17;
+        return st;
+    };
+    const uint64_t thr = (uint64_t)(std::min(p_minor, 0.999999) * 18446744073709551615.0);
+    const size_t ns = std::min<size_t>(xspans.size(), 512);
+    uint32_t carry = 0;
+    for (size_t sp = 0; sp < ns; ++sp) {
+        uint32_t m[4], c[4];
+        for (int w = 0; w < 4; ++w) {
+            uint32_t v = 0;
+            for (int i = 0; i < 32; ++i) v |= (uint32_t)(next() < thr) << i;
+            m[w] = v;
+        }
+        const uint32_t L = compact_span(m, xspans[sp], c);
+        if (!L) continue;
+        const bool has_prev = (sp % per_block) != 0;
+        const PairMasks pm = pair_mismatches(c, xspans[sp].sm, carry, has_prev, (int)L, false);
+        tokenize_pairs(c, xspans[sp].sk, pm, (int)L, false, h);
+        carry = L >= 2 ? ((((c[(L - 1) >> 5] >> ((L - 1) & 31)) & 1u) << 1) | ((c[(L - 2) >> 5] >> ((L - 2) & 31)) & 1u)) : 0u;
+    }
+    return h;
+}
+
+inline FusedTable make_table_x(double p_minor, const std::vector<XSpan>& xspans, int per_block,
+                               const uint64_t* prefix_hist) {
+    HistSink h = simulate_x(p_minor, xspans, per_block);
+    const uint64_t blocks = std::max<uint64_t>(1, std::min<size_t>(xspans.size(), 512) / (size_t)std::max(1, per_block));
+    return finish_cell_table(h, blocks, prefix_hist);
+}
 
 struct ByteHist {
     uint64_t nlit[256] = {0};

@@ -175,6 +175,13 @@ struct FusedStage {
         const uint32_t n1 = t1 >> 24;
         put((t1 & 0xFFFFFFu) | ((t2 & 0xFFFFFFu) << n1), n1 + (t2 >> 24));   // tables keep n1 + n2 <= 32
     }
+    // [gap predicted bytes as one match, gap == 0 or >= 3][literal id]  (k_fused_x.cuh)
+    __device__ __forceinline__ void gap_tok(int gap, int id) {
+        const uint32_t t1 = len_tok[gap];
+        const uint32_t t2 = lit_tok(id);
+        const uint32_t n1 = t1 >> 24;
+        put((t1 & 0xFFFFFFu) | ((t2 & 0xFFFFFFu) << n1), n1 + (t2 >> 24));
+    }
 };
 
 // Slow-path sink (a thread overflowed its staging): ORs every token straight into the zeroed output words.
@@ -199,6 +206,10 @@ struct FusedEmit {
         if (gap == 1) lit(odd ? kLitSlash : kLitTab);
         else if (gap) match(gap);
         lit(bit);
+    }
+    __device__ void gap_tok(int gap, int id) {
+        if (gap) match(gap);
+        lit(id);
     }
 };
 
