@@ -236,6 +236,8 @@ inline FusedTable finish_cell_table(const HistSink& h, uint64_t blocks, const ui
         t.len_tok[len] = ((c & 0xFFFFFFu) | ((uint32_t)(len - kLenBase[ci]) << cl)) | ((cl + ex + 1u) << 24);
     }
     for (int i = 0; i < 5; ++i) t.lit[i] = lc[lit_byte[i]];
+    t.len_tok[1] = lc['\t'];   // a 1-byte gap is the separator before the allele: '\t' before slot 0, '/' before slot 1
+    t.len_tok[2] = lc['/'];
     t.eob = lc[256];
     for (int c = 0; c < 256; ++c) t.pre_lit[c] = lc[c];
     BitString hdr = dynamic_header(ll);

@@ -381,31 +381,37 @@ __global__ void __launch_bounds__(256, 1) k_bgzf_generic(const uint8_t* __restri
 __global__ void __launch_bounds__(1024) k_scan_sizes(const uint32_t* __restrict__ sizes, uint32_t nb,
                                                     uint64_t* __restrict__ offsets, const uint32_t* __restrict__ crcs,
                                                     uint64_t* __restrict__ totals /* [0]=bytes [1]=crc xor */) {
-    __shared__ uint64_t part[1024];
-    __shared__ uint32_t xpart[1024];
-    const uint32_t tid = threadIdx.x;
+    __shared__ uint64_t wsum[32];
+    __shared__ uint32_t wxor[32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
     const uint32_t per = (nb + 1023u) / 1024u;
     const uint32_t b0 = min(nb, tid * per), b1 = min(nb, b0 + per);
     uint64_t sum = 0;
     uint32_t x = 0;
     for (uint32_t i = b0; i < b1; ++i) { sum += sizes[i]; x ^= crcs[i]; }
-    part[tid] = sum;
-    xpart[tid] = x;
+    uint64_t v = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint64_t u = __shfl_up_sync(0xFFFFFFFFu, v, o);
+        if (lane >= (uint32_t)o) v += u;
+    }
+    x = warp_xor(x);
+    if (lane == 31u) { wsum[wid] = v; wxor[wid] = x; }
     __syncthreads();
-    if (tid == 0) {
-        uint64_t run = 0;
-        uint32_t xx = 0;
-        for (int i = 0; i < 1024; ++i) {
-            const uint64_t v = part[i];
-            part[i] = run;
-            run += v;
-            xx ^= xpart[i];
+    if (wid == 0) {
+        const uint64_t w = wsum[lane];
+        uint64_t s2 = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint64_t u = __shfl_up_sync(0xFFFFFFFFu, s2, o);
+            if (lane >= (uint32_t)o) s2 += u;
         }
-        totals[0] = run;
-        totals[1] = xx;
+        wsum[lane] = s2 - w;  // exclusive prefix of the warp totals
+        const uint32_t xx = warp_xor(wxor[lane]);
+        if (lane == 31u) { totals[0] = s2; totals[1] = xx; }
     }
     __syncthreads();
-    uint64_t run = part[tid];
+    uint64_t run = wsum[wid] + v - sum;
     for (uint32_t i = b0; i < b1; ++i) { offsets[i] = run; run += sizes[i]; }
 }
 

@@ -98,16 +98,14 @@ __host__ __device__ __forceinline__ void tokenize_cells(const uint32_t m[4], uin
         if (q & 1) sink.lit((q & 3) == 1 ? kLitSlash : kLitTab);
         else sink.lit((int)((pick4(m, q >> 6) >> ((q >> 1) & 31)) & 1u));
     };
-    int cw = 0;
-    uint32_t cx = c.x[0], cm = m[0];
-    for (;;) {
-        if (!cx) {
-            if (cw == 3) break;
-            ++cw;
-            cx = cw == 1 ? c.x[1] : (cw == 2 ? c.x[2] : c.x[3]);
-            cm = cw == 1 ? m[1] : (cw == 2 ? m[2] : m[3]);
-            continue;
-        }
+    // walk the set bits of the 128-bit mismatch mask; moving on to the next non-empty word is a few predicated
+    // selects at the end of an iteration, not an iteration of its own, so sparse spans do not pay for it
+    auto next_word = [&](int from) {  // first non-empty word with index >= from, 4 when none
+        return (from <= 0 && c.x[0]) ? 0 : ((from <= 1 && c.x[1]) ? 1 : ((from <= 2 && c.x[2]) ? 2 : ((from <= 3 && c.x[3]) ? 3 : 4)));
+    };
+    int cw = next_word(0);
+    uint32_t cx = pick4(c.x, cw), cm = pick4(m, cw);
+    while (cw < 4) {
 #ifdef __CUDA_ARCH__
         const int b = __ffs((int)cx) - 1;
 #else
@@ -123,6 +121,11 @@ __host__ __device__ __forceinline__ void tokenize_cells(const uint32_t m[4], uin
         }
         sink.gap_lit(gap, b & 1, (int)((cm >> b) & 1u));
         prev_end = p + 1;
+        if (!cx) {
+            cw = next_word(cw + 1);
+            cx = pick4(c.x, cw);
+            cm = pick4(m, cw);
+        }
     }
     {   // tail: bytes [prev_end, end) are predicted
         const int gap = end - prev_end;
@@ -170,7 +173,8 @@ struct FusedStage {
         put(t & 0xFFFFFFu, t >> 24);
     }
     __device__ __forceinline__ void gap_lit(int gap, int odd, int bit) {
-        const uint32_t t1 = gap == 1 ? (odd ? lit_slash : lit_tab) : len_tok[gap];  // len_tok[0] is the empty token
+        // len_tok[0] is the empty token, len_tok[1] / len_tok[2] hold the '\t' / '/' literal (gap 2 never gets here)
+        const uint32_t t1 = len_tok[gap + (gap == 1 ? odd : 0)];
         const uint32_t t2 = bit ? lit1 : lit0;
         const uint32_t n1 = t1 >> 24;
         put((t1 & 0xFFFFFFu) | ((t2 & 0xFFFFFFu) << n1), n1 + (t2 >> 24));   // tables keep n1 + n2 <= 32
