@@ -180,6 +180,14 @@ struct HistSink {
         if (gap) match(gap);
         lit(id);
     }
+    void fused3(int gap, int id_a, int id_b, int id) {
+        if (gap >= 3) match(gap);
+        else {
+            if (gap >= 1) lit(id_a);
+            if (gap == 2) lit(id_b);
+        }
+        lit(id);
+    }
 };
 
 // Token statistics of `blocks` full segments (255 spans of 64 cells) of Bernoulli(p_minor) alleles.
@@ -220,10 +228,10 @@ inline FusedTable finish_cell_table(const HistSink& h, uint64_t blocks, const ui
         for (int c = 0; c < 256; ++c)
             if (prefix_hist[c]) f[c] += std::max<uint64_t>(1, prefix_hist[c]);
     std::vector<uint8_t> ll = huff_lengths(f, 15);
-    // the kernels fuse [match or separator][literal] into one 32-bit token: keep the cell literals <= 11 bits
-    while (ll['0'] > 11 || ll['1'] > 11 || ll['/'] > 11 || ll['\t'] > 11) {
+    // the kernels fuse [match or separator][literal] into one 32-bit token: keep the cell literals <= 10 bits
+    while (ll['0'] > 10 || ll['1'] > 10 || ll['/'] > 10 || ll['\t'] > 10) {
         for (uint8_t c : {(uint8_t)'0', (uint8_t)'1', (uint8_t)'/', (uint8_t)'\t'})
-            if (ll[c] > 11) f[c] *= 4;
+            if (ll[c] > 10) f[c] *= 4;
         ll = huff_lengths(f, 15);
     }
     std::vector<uint32_t> lc = huff_codes(ll);

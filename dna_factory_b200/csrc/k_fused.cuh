@@ -181,10 +181,19 @@ struct FusedStage {
     }
     // [gap predicted bytes as one match, gap == 0 or >= 3][literal id]  (k_fused_x.cuh)
     __device__ __forceinline__ void gap_tok(int gap, int id) {
-        const uint32_t t1 = len_tok[gap];
+        const uint32_t t1 = gap ? len_tok[gap] : 0u;
         const uint32_t t2 = lit_tok(id);
         const uint32_t n1 = t1 >> 24;
         put((t1 & 0xFFFFFFu) | ((t2 & 0xFFFFFFu) << n1), n1 + (t2 >> 24));
+    }
+    // [match of gap >= 3 bytes | literal id_a if gap >= 1, literal id_b if gap == 2 | nothing][literal id] as ONE
+    // token, branch-free (tables keep cell literals <= 10 bits and matches <= 21, so the sum fits 32 bits)
+    __device__ __forceinline__ void fused3(int gap, int id_a, int id_b, int id) {
+        const uint32_t t1 = gap >= 3 ? len_tok[gap] : (gap >= 1 ? lit_tok(id_a) : 0u);
+        const uint32_t t2 = gap == 2 ? lit_tok(id_b) : 0u;
+        const uint32_t t3 = lit_tok(id);
+        const uint32_t n1 = t1 >> 24, n2 = n1 + (t2 >> 24);
+        put((t1 & 0xFFFFFFu) | ((t2 & 0xFFFFFFu) << n1) | ((t3 & 0xFFFFFFu) << n2), n2 + (t3 >> 24));
     }
 };
 
@@ -213,6 +222,14 @@ struct FusedEmit {
     }
     __device__ void gap_tok(int gap, int id) {
         if (gap) match(gap);
+        lit(id);
+    }
+    __device__ void fused3(int gap, int id_a, int id_b, int id) {
+        if (gap >= 3) match(gap);
+        else {
+            if (gap >= 1) lit(id_a);
+            if (gap == 2) lit(id_b);
+        }
         lit(id);
     }
 };

@@ -81,7 +81,7 @@ __host__ __device__ __forceinline__ PairMasks pair_mismatches(const uint32_t c[4
 }
 
 // Tokens of a span given as (compacted alleles, separator kinds, mismatch masks).  Sink: gap_tok(gap, lit id)
-// with gap == 0 or >= 3, lit(id), match(len).
+// fused3(gap, id_a, id_b, id): [match gap>=3 | literals id_a (gap>=1), id_b (gap==2)][literal id]; lit(id); match(len).
 template <class Sink>
 __host__ __device__ __forceinline__ void tokenize_pairs(const uint32_t c[4], const uint32_t sk[4], const PairMasks& pm, int L,
                                                         bool ends_row, Sink& sink) {
@@ -92,44 +92,36 @@ __host__ __device__ __forceinline__ void tokenize_pairs(const uint32_t c[4], con
         const uint32_t bit = (pick4((q & 1) ? sk : c, q >> 6) >> ((q >> 1) & 31)) & 1u;
         return (q & 1) ? (bit ? kLitSlash : kLitTab) : (int)bit;
     };
-    auto event = [&](int p, int id) {  // literal `id` at byte p, preceded by predicted bytes [prev_end, p)
-        int gap = p - prev_end;
-        if (gap == 1 || gap == 2) {
-            for (int q = prev_end; q < p; ++q) sink.lit(lit_id_at(q));
-            gap = 0;
-        }
-        sink.gap_tok(gap, id);
-        prev_end = p + 1;
+    // One mismatching byte per iteration (an allele byte before the separator of the same pair), every case
+    // through the same straight-line code: [match | 1-2 spelled-out predicted bytes | nothing][literal].
+    auto word_of = [&](const uint32_t* a, const uint32_t* b2, int w) { return pick4(a, w) | pick4(b2, w); };
+    auto next_word = [&](int from) {  // first word with an event, index >= from; 4 when none
+        return (from <= 0 && word_of(pm.xc, pm.sm, 0)) ? 0 : ((from <= 1 && word_of(pm.xc, pm.sm, 1)) ? 1
+             : ((from <= 2 && word_of(pm.xc, pm.sm, 2)) ? 2 : ((from <= 3 && word_of(pm.xc, pm.sm, 3)) ? 3 : 4)));
     };
-    int cw = 0;
-    uint32_t ce = pm.xc[0] | pm.sm[0], ca = pm.xc[0], cc = c[0], ck = sk[0];
-    for (;;) {
-        if (!ce) {
-            if (cw == 3) break;
-            ++cw;
-            ca = cw == 1 ? pm.xc[1] : (cw == 2 ? pm.xc[2] : pm.xc[3]);
-            ce = ca | (cw == 1 ? pm.sm[1] : (cw == 2 ? pm.sm[2] : pm.sm[3]));
-            cc = cw == 1 ? c[1] : (cw == 2 ? c[2] : c[3]);
-            ck = cw == 1 ? sk[1] : (cw == 2 ? sk[2] : sk[3]);
-            continue;
-        }
+    int cw = next_word(0);
+    uint32_t ca = pick4(pm.xc, cw), cs = pick4(pm.sm, cw), cc = pick4(c, cw), ck = pick4(sk, cw);
+    while (cw < 4) {
+        const uint32_t ce = ca | cs;
 #ifdef __CUDA_ARCH__
         const int b = __ffs((int)ce) - 1;
 #else
         const int b = __builtin_ctz(ce);
 #endif
-        ce &= ce - 1;
-        const int k2 = 2 * (32 * cw + b);
-        const int sep_id = ((ck >> b) & 1u) ? kLitSlash : kLitTab;
-        if ((ca >> b) & 1u) {
-            event(k2, (int)((cc >> b) & 1u));
-            const uint32_t smw = cw == 0 ? pm.sm[0] : (cw == 1 ? pm.sm[1] : (cw == 2 ? pm.sm[2] : pm.sm[3]));
-            if ((smw >> b) & 1u) {
-                sink.lit(sep_id);
-                prev_end = k2 + 2;
-            }
-        } else {
-            event(k2 + 1, sep_id);
+        const uint32_t is_a = (ca >> b) & 1u;
+        ca &= ~(is_a << b);
+        cs &= ~((is_a ^ 1u) << b);
+        const int p = 2 * (32 * cw + b) + (int)(is_a ^ 1u);
+        const int id = is_a ? (int)((cc >> b) & 1u) : (((ck >> b) & 1u) ? kLitSlash : kLitTab);
+        const int gap = p - prev_end;
+        sink.fused3(gap, lit_id_at(prev_end), lit_id_at(prev_end + 1), id);
+        prev_end = p + 1;
+        if (!(ca | cs)) {
+            cw = next_word(cw + 1);
+            ca = pick4(pm.xc, cw);
+            cs = pick4(pm.sm, cw);
+            cc = pick4(c, cw);
+            ck = pick4(sk, cw);
         }
     }
     {
@@ -217,8 +209,8 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 3) k_fused_x(const XArgs xa)
     const bool my_end_row = ends_row && nc > 0 && 64u * tid + (uint32_t)nc == d.ncells;
     if (nc > 0) {
         const PairMasks pmk = pair_mismatches(c, xs->sm, carry, tid > 0, (int)L, my_end_row);
-        key = __popc(pmk.xc[0] | pmk.sm[0]) + __popc(pmk.xc[1] | pmk.sm[1]) + __popc(pmk.xc[2] | pmk.sm[2]) +
-              __popc(pmk.xc[3] | pmk.sm[3]);
+        key = (__popc(pmk.xc[0]) + __popc(pmk.sm[0]) + __popc(pmk.xc[1]) + __popc(pmk.sm[1]) + __popc(pmk.xc[2]) +
+               __popc(pmk.sm[2]) + __popc(pmk.xc[3]) + __popc(pmk.sm[3]) + 1) >> 1;   // mismatching bytes / 2: 0..128
         rank_in_bin = atomicAdd(&s.cnt[key], 1u);
     }
     // ---- CRC32 share of this span: template ^ delta, shifted to the block end
