@@ -34,7 +34,7 @@ TOTAL_SNPS = 5_000_000
 MIN_MAF = 0.01
 LEVEL = 2
 MALE_ODDS = 0.5
-ROWS_PER_STEP = 8192
+ROWS_PER_STEP = 32768
 PHILOX_SEED = 0x5EED000000000001
 HOST_SEED = 20260101
 E2E_CHUNK = 320 << 20
@@ -92,7 +92,7 @@ class ClockSampler(threading.Thread):
                 except Exception:
                     r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
                 self.samples.append((time.perf_counter(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), r))
-                time.sleep(0.002)
+                time.sleep(0.005)
         except Exception as e:  # noqa: clocks are reported as unknown, never fatal
             self.error = "unavailable:%s" % type(e).__name__
 
@@ -122,7 +122,8 @@ def cpu_reference_run(steps, warmup, budget_s=20.0):
     Each step is a bounded sample of the workload (same sample count and level, fewer SNP rows)."""
     from oracle import oracle
     oracle.build()
-    cores = oracle.lib().dnaf_or_num_threads()
+    # every host thread the box offers, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1)
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     rows = 64
     sex, ctl, table, orow, osamp = synth_population(rows * (steps + warmup), window=rows)
     snps_all = table.to_snps()

@@ -8,6 +8,7 @@
 //   sample -> (overrides) -> format -> BGZF encode -> scan -> compact -> D2H -> sink      (generic path)
 // or the fused kernel (k_fused.cuh) followed by scan -> compact -> D2H -> sink.
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -830,7 +831,9 @@ int generate_impl(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t se
     while (r0 < row_end) {
         const uint64_t r1 = next_chunk_end(c, r0, row_end, c->chunk_bytes);
         dnaf_ctx::OutBuf& B = c->ob[cur];
+        const auto t_plan0 = std::chrono::steady_clock::now();
         plan_pass(c, r0, r1, c->h_k.data());
+        const auto t_plan1 = std::chrono::steady_clock::now();
         c->cur_ob = cur;
         rc = reserve_outputs(c, B, c->pass_blocks);
         if (!rc) rc = reserve_stage(c, B);
@@ -940,6 +943,12 @@ int generate_impl(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t se
         B.fused = !c->fplan.empty() || !c->tplan.empty() || !c->xplan.empty();
         rc = close_pass(c, B, c->pass_blocks, &local);
         if (rc) return rc;
+        if (getenv("DNAF_TRACE")) {
+            const auto t_l = std::chrono::steady_clock::now();
+            fprintf(stderr, "[dnaf] pass rows %llu: plan %.0f us, launch %.0f us\n", (unsigned long long)(r1 - r0),
+                    std::chrono::duration<double, std::micro>(t_plan1 - t_plan0).count(),
+                    std::chrono::duration<double, std::micro>(t_l - t_plan1).count());
+        }
         // the previous pass is copied out while this one computes
         if (pending >= 0) {
             rc = retire_pass(c, c->ob[pending], sink, &local);
