@@ -166,6 +166,12 @@ struct dnaf_ctx {
     std::vector<uint64_t> tables_sig;      // what d_ftables currently holds
     std::vector<uint8_t> h_sex;
     DevBuf d_crc4, d_xspan, d_tdesc, d_xspans, d_xdesc;
+    // k_auto (k_auto.cuh): code tables + byte LUTs per (bucket, starts-row), CRC move tables, per-row prefix CRCs
+    DevBuf d_atables, d_etab2, d_mtab, d_mtail, d_mpre, d_xinit, d_pre_crc;
+    std::map<std::pair<uint64_t, uint64_t>, AutoTable> atable_cache;
+    std::vector<uint32_t> h_mtail, h_mpre;
+    bool seg_tabs_dirty = false;
+    std::vector<uint8_t> h_pfx_tab;        // per row: prefix ends with '\t' (k_auto's first match may reach into it)
     std::vector<XSpan> h_xspans;
     std::vector<uint32_t> h_seg_crc_x;     // L(template body) per X segment
     std::vector<uint32_t> h_xoff;
@@ -242,6 +248,12 @@ int ensure_layout(dnaf_ctx* c) {
     int rc = upload(c, c->d_row_off, c->h_row_off.data(), c->S + 1);
     if (rc) return rc;
     build_segments(c);
+    if (c->seg_tabs_dirty) {
+        rc = upload(c, c->d_mtail, c->h_mtail.data(), c->h_mtail.size());
+        if (!rc) rc = upload(c, c->d_mpre, c->h_mpre.data(), c->h_mpre.size());
+        if (rc) return rc;
+        c->seg_tabs_dirty = false;
+    }
     rc = ensure_tables(c);
     if (rc) return rc;
     c->layout_ok = true;
@@ -335,6 +347,10 @@ int ensure_tables(dnaf_ctx* c) {
     if (sig != c->tables_sig) {
         std::vector<FusedTable> tabs((size_t)nb * kVariants);
         memset(tabs.data(), 0, tabs.size() * sizeof(FusedTable));
+        std::vector<AutoTable> atabs((size_t)nb * 2);
+        memset(atabs.data(), 0, atabs.size() * sizeof(AutoTable));
+        const int per_block = (int)std::max<size_t>(1, c->h_seg_cell0.size() > 1
+                                                           ? (c->h_seg_cell0[1] - c->h_seg_cell0[0] + 63) / 64 : 1);
         for (int b = 0; b < nb; ++b) {
             const double p = c->bucket_p[b];
             uint64_t pbits;
@@ -342,6 +358,17 @@ int ensure_tables(dnaf_ctx* c) {
             for (int v = 0; v < kVariants; ++v) {
                 if (!need[b * kVariants + v]) continue;
                 const bool with_prefix = (v & 1) == 0;
+                if (v < 2) {   // autosome rows: k_auto's tables
+                    auto key = std::make_pair(pbits, (with_prefix ? c->ph_hash : 0x5bd1e995ull) * 31 + (uint64_t)per_block);
+                    auto it = c->atable_cache.find(key);
+                    if (it == c->atable_cache.end()) {
+                        AutoTable t = hosttab::make_auto_table(p, with_prefix ? c->ph.data() : nullptr, per_block, with_prefix);
+                        if (t.hdr_bits == 0xFFFFFFFFu) return DNAF_OK;  // header too long: stay on the generic path
+                        it = c->atable_cache.emplace(key, t).first;
+                    }
+                    atabs[(size_t)b * 2 + v] = it->second;
+                    continue;
+                }
                 const int cls = v < 2 ? -1 : (v >= 10 ? 100 : (v - 2) / 2);   // -1: autosome cells, 100: X cells
                 const uint64_t vkey = (with_prefix ? c->ph_hash : 0x5bd1e995ull) * 31 + (uint64_t)(cls + 1) * 1000003ull +
                                       (cls >= 0 ? c->samples_epoch * 0x9E3779B97F4A7C15ull : 0);
@@ -349,9 +376,7 @@ int ensure_tables(dnaf_ctx* c) {
                 auto it = c->table_cache.find(key);
                 if (it == c->table_cache.end()) {
                     const uint64_t* hist = with_prefix ? c->ph.data() : nullptr;
-                    const int per_block = (int)std::max<size_t>(1, c->h_seg_cell0.size() > 1
-                                                                       ? (c->h_seg_cell0[1] - c->h_seg_cell0[0] + 63) / 64 : 1);
-                    FusedTable t = cls < 0 ? hosttab::make_table(p, hist)
+                        FusedTable t = cls < 0 ? hosttab::make_table(p, hist)
                                    : cls == 100 ? hosttab::make_table_x(p, c->h_xspans, per_block, hist)
                                                 : hosttab::make_text_table(cls, p, c->h_sex.data(), c->n, hist);
                     if (t.hdr_bits == 0xFFFFFFFFu) return DNAF_OK;  // header too long: stay on the generic path
@@ -361,6 +386,7 @@ int ensure_tables(dnaf_ctx* c) {
             }
         }
         int rc = upload(c, c->d_ftables, tabs.data(), tabs.size());
+        if (!rc) rc = upload(c, c->d_atables, atabs.data(), atabs.size());
         if (rc) return rc;
         c->tables_sig = sig;
     }
@@ -388,6 +414,35 @@ int ensure_tables(dnaf_ctx* c) {
                 }
         int rc = upload(c, c->d_etab, etab.data(), etab.size());
         if (rc) return rc;
+        {   // k_auto: E table measured to one byte before the span's cell end; moves by whole spans; init terms
+            std::vector<uint32_t> etab2(16 * 256, 0);
+            for (int w = 0; w < 4; ++w)
+                for (int k = 0; k < 4; ++k)
+                    for (int b = 0; b < 256; ++b) {
+                        uint32_t v = 0;
+                        for (int i = 0; i < 8; ++i)
+                            if ((b >> i) & 1) {
+                                const int j = 32 * w + 8 * k + i;
+                                v ^= hosttab::mulmod(xp[254 - 2 * j], tab[1]);
+                            }
+                        etab2[(4 * w + k) * 256 + b] = v;
+                    }
+            rc = upload(c, c->d_etab2, etab2.data(), etab2.size());
+            if (rc) return rc;
+            std::vector<uint32_t> mtab((size_t)254 * 1024);
+            uint32_t xj = 0x80000000u;   // x^(8*256*j)
+            for (int j = 0; j < 254; ++j) {
+                hosttab::fill_mul_table(xj, &mtab[(size_t)j * 1024]);
+                xj = hosttab::mulmod(xj, xp[256]);
+            }
+            rc = upload(c, c->d_mtab, mtab.data(), mtab.size());
+            if (rc) return rc;
+            std::vector<uint32_t> xinit(kBlk + 1);
+            xinit[0] = 0xFFFFFFFFu;
+            for (uint32_t i = 1; i <= kBlk; ++i) xinit[i] = tab[xinit[i - 1] & 0xFFu] ^ (xinit[i - 1] >> 8);
+            rc = upload(c, c->d_xinit, xinit.data(), xinit.size());
+            if (rc) return rc;
+        }
         // slicing-by-4 tables for k_fused_text
         std::vector<uint32_t> c4(1024);
         for (int i = 0; i < 256; ++i) c4[i] = tab[i];
@@ -428,10 +483,25 @@ void build_segments(dnaf_ctx* c) {
         const uint32_t cnt = std::min(c->n, (sg + 1) * per * 64u) - cell;
         if (!cnt) break;
         c->h_seg_cell0.push_back(cell);
-        c->h_seg_crc.push_back(raw_crc(&body[4ull * cell], 4ull * cnt, tab.data()));
+        // k_auto's blocks: a segment starts with the separator that ended the previous one and stops before its own
+        // last separator, unless it ends the row
+        const uint64_t b0 = sg ? 4ull * cell - 1 : 0, b1 = (cell + cnt == c->n) ? 4ull * c->n : 4ull * (cell + cnt) - 1;
+        c->h_seg_crc.push_back(raw_crc(&body[b0], b1 - b0, tab.data()));
     }
     c->h_seg_cell0.push_back(c->n);
     c->fused_threads = std::max(64u, (per + 31u) / 32u * 32u);
+    {   // CRC move tables that depend on the sample count: the short last span, and prefix -> end of segment 0
+        std::vector<uint32_t> xp(4ull * c->n + 2);
+        xp[0] = 0x80000000u;
+        for (size_t k = 1; k < xp.size(); ++k) xp[k] = (xp[k - 1] >> 8) ^ tab[xp[k - 1] & 0xFFu];   // times x^8
+        c->h_mtail.assign(1024, 0);
+        c->h_mpre.assign(2048, 0);
+        hosttab::fill_mul_table(xp[4u * (c->n & 63u)], c->h_mtail.data());
+        const uint32_t cells0 = c->h_seg_cell0[1] - c->h_seg_cell0[0];
+        hosttab::fill_mul_table(xp[4ull * cells0 - 1], c->h_mpre.data());
+        hosttab::fill_mul_table(xp[4ull * cells0], c->h_mpre.data() + 1024);
+        c->seg_tabs_dirty = true;
+    }
     {   // X rows use the same sample segments; their template is the all-reference X body
         std::vector<uint8_t> xbody;
         xbody.reserve(c->body[kX]);
@@ -465,7 +535,7 @@ void build_segments(dnaf_ctx* c) {
 inline int row_kind(const dnaf_ctx* c, uint64_t r, const uint8_t* hk) {
     if (!c->fused || !c->fused_ok || c->h_plen[r] < 1 || c->h_plen[r] > 64 || c->n == 0) return 0;
     if (c->body[c->h_cls[r]] < kFusedMinRowBytes) return 0;
-    if (hk[r] <= 2 && c->h_cls[r] == kAuto) return 1;
+    if (hk[r] <= 2 && c->h_cls[r] == kAuto) return c->h_pfx_tab[r] ? 1 : 2;
     if (hk[r] <= 2 && c->h_cls[r] == kX) return 3;
     return 2;
 }
@@ -525,7 +595,7 @@ void plan_pass(dnaf_ctx* c, uint64_t r0, uint64_t r1, const uint8_t* hk) {
                 d.ovr_first = (uint32_t)o;
                 d.ovr_count = (uint32_t)(oe - o);
                 if (kind == 1) {
-                    d.table = (uint32_t)c->h_bucket[r] * kVariants + (sgi == 0 ? 0u : 1u);
+                    d.table = (uint32_t)c->h_bucket[r] * 2u + (sgi == 0 ? 0u : 1u);
                     d.body_crc = c->h_seg_crc[sgi];
                     c->fplan.push_back(d);
                 } else {
@@ -890,14 +960,18 @@ int generate_impl(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t se
         if (!c->fplan.empty()) {
             rc = upload_async(c, c->d_fdesc, c->fplan);
             if (rc) return rc;
-            FusedArgs fa;
+            AutoArgs fa;
             fa.sv = sample_view(c);
             fa.nv = snp_view(c);
             fa.desc = c->d_fdesc.as<FusedDesc>();
-            fa.tables = c->d_ftables.as<FusedTable>();
-            fa.etab = c->d_etab.as<uint32_t>();
+            fa.tables = c->d_atables.as<AutoTable>();
+            fa.etab = c->d_etab2.as<uint32_t>();
+            fa.mtab = c->d_mtab.as<uint32_t>();
+            fa.mtail = c->d_mtail.as<uint32_t>();
+            fa.mpre = c->d_mpre.as<uint32_t>();
             fa.crctab = c->d_crctab.as<uint32_t>();
-            fa.xpow8 = c->d_xpow8.as<uint32_t>();
+            fa.xinit = c->d_xinit.as<uint32_t>();
+            fa.pre_crc = c->d_pre_crc.as<uint32_t>();
             fa.orow = c->d_orow.as<uint64_t>();
             fa.osamp = c->d_osamp.as<uint32_t>();
             fa.row_base = c->row_base;
@@ -906,7 +980,7 @@ int generate_impl(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t se
             fa.slots = c->d_slots.as<uint8_t>();
             fa.sizes = c->d_sizes.as<uint32_t>();
             fa.crcs = c->d_crcs.as<uint32_t>();
-            k_fused_auto<<<(uint32_t)c->fplan.size(), c->fused_threads, 0, c->stream>>>(fa);
+            k_auto<<<(uint32_t)c->fplan.size(), c->fused_threads, auto_smem_bytes(c->fused_threads), c->stream>>>(fa);
             local.kernel_launches += 1;
             CU(c, cudaGetLastError());
         }
@@ -1152,7 +1226,11 @@ int dnaf_set_snps(dnaf_ctx* c, uint64_t S, const uint8_t* cls, const uint8_t* k,
     c->h_cls.assign(cls, cls + S);
     c->h_k.assign(k, k + S);
     c->h_plen.resize(S);
-    for (uint64_t r = 0; r < S; ++r) c->h_plen[r] = (uint32_t)(pre_off[r + 1] - pre_off[r]);
+    c->h_pfx_tab.resize(S);
+    for (uint64_t r = 0; r < S; ++r) {
+        c->h_plen[r] = (uint32_t)(pre_off[r + 1] - pre_off[r]);
+        c->h_pfx_tab[r] = c->h_plen[r] && prefix[pre_off[r + 1] - 1] == '\t';
+    }
     // pageable sources: each copy returns once the data is staged, one synchronise covers them all
     int rc = upload(c, c->d_cls, cls, S, false);
     if (!rc) rc = upload(c, c->d_k, k, S, false);
@@ -1164,6 +1242,11 @@ int dnaf_set_snps(dnaf_ctx* c, uint64_t S, const uint8_t* cls, const uint8_t* k,
         const uint64_t zero = 0;
         rc = upload(c, c->d_pre_off, &zero, 1);
         if (rc) return rc;
+    } else {   // per-row linear CRC of the prefix (k_auto adds it to its blocks' checksums with four lookups)
+        CU(c, c->d_pre_crc.reserve(S * sizeof(uint32_t)));
+        k_prefix_crc<<<(uint32_t)((S + 255) / 256), 256, 0, c->stream>>>(c->d_prefix.as<uint8_t>(), c->d_pre_off.as<uint64_t>(), S,
+                                                                       c->d_crctab.as<uint32_t>(), c->d_pre_crc.as<uint32_t>());
+        CU(c, cudaGetLastError());
     }
     c->have_snps = true;
     c->layout_ok = false;

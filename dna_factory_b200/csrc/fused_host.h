@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "k_fused.cuh"
+#include "k_auto.cuh"
 #include "k_fused_text.cuh"
 #include "k_fused_x.cuh"
 
@@ -258,6 +259,106 @@ inline FusedTable finish_cell_table(const HistSink& h, uint64_t blocks, const ui
 inline FusedTable make_table(double p_minor, const uint64_t* prefix_hist) {
     const int kBlocks = 4;
     return finish_cell_table(simulate(p_minor, kBlocks), kBlocks, prefix_hist);
+}
+
+// ---- k_auto (k_auto.cuh): token statistics under its span grammar, code tables and the byte LUT ----
+struct AutoHistSink {
+    HistSink h;
+    void tok(int gap) {
+        if (gap == 1) h.lit(kLitTab);
+        else if (gap >= 3) h.match(gap);
+    }
+    void lit(int id) { h.lit(id); }
+    void eob() {}
+};
+
+// Token statistics of `blocks` blocks of `per_block` full spans of Bernoulli(p_minor) alleles.
+inline HistSink simulate_auto(double p_minor, int blocks, int per_block, bool starts_row) {
+    AutoHistSink s;
+    uint64_t st = 0x9E3779B97F4A7C15ull ^ (uint64_t)(p_minor * 1e9);
+    auto next = [&]() {
+        st ^= st << 13; st ^= st >> 7; st ^= st << 17;
+        return st;
+    };
+    const uint64_t thr = (uint64_t)(std::min(p_minor, 0.999999) * 18446744073709551615.0);
+    for (int b = 0; b < blocks; ++b) {
+        uint32_t carry = 0;
+        for (int sp = 0; sp < per_block; ++sp) {
+            uint32_t m[4];
+            for (int w = 0; w < 4; ++w) {
+                uint32_t v = 0;
+                for (int i = 0; i < 32; ++i) v |= (uint32_t)(next() < thr) << i;
+                m[w] = v;
+            }
+            span_tokens_ref(m, sp ? carry : (m[0] & 3u), sp == 0, starts_row, 64, false, sp + 1 == per_block, s);
+            carry = m[3] >> 30;
+        }
+    }
+    return s.h;
+}
+
+// Multiply-by-x^(8*bytes) table [4][256] for reflected CRC values (linear: built from the 32 basis bits).
+inline void fill_mul_table(uint32_t xpow /* x^(8*bytes) */, uint32_t* out /* [1024] */) {
+    uint32_t basis[32];
+    for (int i = 0; i < 32; ++i) basis[i] = mulmod(xpow, 1u << i);
+    for (int k = 0; k < 4; ++k)
+        for (int b = 0; b < 256; ++b) {
+            uint32_t v = 0;
+            for (int i = 0; i < 8; ++i)
+                if ((b >> i) & 1) v ^= basis[8 * k + i];
+            out[256 * k + b] = v;
+        }
+}
+
+inline AutoTable make_auto_table(double p_minor, const uint64_t* prefix_hist, int per_block, bool starts_row) {
+    const int kBlocks = std::max(2, 1024 / std::max(1, per_block));
+    const FusedTable f = finish_cell_table(simulate_auto(p_minor, kBlocks, std::max(1, per_block), starts_row), kBlocks, prefix_hist);
+    AutoTable t;
+    memset(&t, 0, sizeof t);
+    if (f.hdr_bits == 0xFFFFFFFFu) {
+        t.hdr_bits = f.hdr_bits;
+        return t;
+    }
+    for (int i = 0; i < 260; ++i) t.len_tok[i] = f.len_tok[i];
+    t.len_tok[0] = 0;
+    t.len_tok[1] = f.lit[kLitTab];
+    t.len_tok[2] = 0;  // even gaps of 2 never reach the table
+    for (int bit = 0; bit < 2; ++bit) {
+        const uint32_t a = f.lit[kLitSlash], b = f.lit[bit];
+        t.len_tok[259 + bit] = ((a & 0xFFFFFFu) | ((b & 0xFFFFFFu) << (a >> 24))) | (((a >> 24) + (b >> 24)) << 24);
+    }
+    for (int i = 0; i < 8; ++i) t.lit[i] = f.lit[i];
+    t.eob = f.eob;
+    t.hdr_bits = f.hdr_bits;
+    memcpy(t.hdr, f.hdr, sizeof t.hdr);
+    memcpy(t.pre_lit, f.pre_lit, sizeof t.pre_lit);
+    for (uint32_t idx = 0; idx < 1024; ++idx) {
+        const uint32_t mb = idx >> 2, xb = (mb ^ idx) & 0xFFu;
+        if (!xb) continue;
+        unsigned __int128 code = 0;
+        uint32_t nb = 0;
+        int first = -1, pe = -1;
+        auto put = [&](uint32_t tok) {
+            if (nb < 100) code |= (unsigned __int128)(tok & 0xFFFFFFu) << nb;
+            nb += tok >> 24;
+        };
+        for (int s = 0; s < 8; ++s) {
+            if (!((xb >> s) & 1u)) continue;
+            if (first < 0) first = s;
+            else {
+                const int g = 2 * s - pe;
+                put(g == 1 ? f.lit[(s & 1) ? kLitSlash : kLitTab] : t.len_tok[g]);
+            }
+            put(f.lit[(mb >> s) & 1u]);
+            pe = 2 * s + 1;
+        }
+        const bool is_long = nb > 43;
+        const uint64_t c = is_long ? 0 : (uint64_t)code;
+        t.lut[idx].x = (uint32_t)c;
+        t.lut[idx].y = (uint32_t)((c >> 32) & 0x7FFu) | ((is_long ? kLutLong : nb) << 11) | ((uint32_t)(2 * first) << 17) |
+                       ((uint32_t)pe << 21);
+    }
+    return t;
 }
 
 // Static per-population description of the X-row spans (k_fused_x.cuh): compaction masks (Hacker's Delight
