@@ -11,6 +11,8 @@ constexpr uint32_t kBlk = 65280;      // uncompressed bytes per BGZF block (htsl
 constexpr uint32_t kSpan = 256;       // bytes of text one thread tokenises; a whole span is one match at most
 constexpr uint32_t kSlot = 65536;     // a BGZF block never exceeds 64 KiB
 constexpr uint32_t kCrcPoly = 0xEDB88320u;
+// Slot layout: the BGZF block starts at slot + 14, so that its deflate payload (slot + 32) is 16-byte aligned.
+constexpr uint32_t kSlotLead = 14;
 
 enum : uint8_t { kAuto = 0, kX = 1, kY = 2, kMT = 3 };
 

@@ -352,11 +352,11 @@ inline AutoTable make_auto_table(double p_minor, const uint64_t* prefix_hist, in
             put(f.lit[(mb >> s) & 1u]);
             pe = 2 * s + 1;
         }
-        const bool is_long = nb > 43;
+        const bool is_long = nb > kLutMaxBits;
         const uint64_t c = is_long ? 0 : (uint64_t)code;
         t.lut[idx].x = (uint32_t)c;
-        t.lut[idx].y = (uint32_t)((c >> 32) & 0x7FFu) | ((is_long ? kLutLong : nb) << 11) | ((uint32_t)(2 * first) << 17) |
-                       ((uint32_t)pe << 21);
+        t.lut[idx].y = (uint32_t)((c >> 32) & 0x7FFu) | (is_long ? kLutLong : (nb << 11)) | ((uint32_t)(2 * first) << 24) |
+                       ((uint32_t)pe << 28);
     }
     return t;
 }

@@ -24,18 +24,25 @@
 namespace dnaf {
 
 constexpr int kAStage = 16;          // staged words per span before the block falls back to direct emission
-constexpr uint32_t kLutLong = 63u;   // nbits value of a LUT entry whose bit string does not fit
+#ifndef DNAF_LUT_MAX_BITS
+#define DNAF_LUT_MAX_BITS 43
+#endif
+constexpr uint32_t kLutMaxBits = DNAF_LUT_MAX_BITS;   // interior bits a LUT entry can hold (a <= 21-bit match token rides along in 64)
+constexpr uint32_t kLutLong = 1u << 17;               // flag of a LUT entry whose bit string does not fit
 
 // Static code tables of one (MAF bucket, with/without prefix) pair.
 struct AutoTable {
+    // ---- first kATabWords words + the LUT are copied to shared memory by every block (cp.async, 16-byte units)
     uint32_t len_tok[264];   // [g] token bridging g predicted bytes: 0 empty, 1 '\t' literal, 3..258 match; [259 + bit]: '/' + allele literal
     uint32_t lit[8];         // cell literals by id: code | bits << 24
     uint32_t eob;
     uint32_t hdr_bits;
-    uint32_t hdr[62];
+    uint32_t hdr[62];        // serialized dynamic-block header
+    uint2 lut[1024];         // x: code bits 0..31; y: code bits 32..42 | nbits << 11 | long << 17 | 2*first << 24 | (2*last+1) << 28
     uint32_t pre_lit[256];   // literal codes of prefix bytes
-    uint2 lut[1024];         // x: code bits 0..31; y: code bits 32..42 | nbits << 11 | 2*first << 17 | (2*last+1) << 21
 };
+constexpr uint32_t kATabWords = 264 + 8 + 2 + 62;   // 336 words = 84 x 16 bytes
+static_assert(kATabWords % 4 == 0 && sizeof(AutoTable) % 16 == 0, "AutoTable must copy in 16-byte units");
 
 struct AutoArgs {
     SampleView sv;
@@ -117,7 +124,9 @@ struct AStage {
         }
         nacc += n;
         const uint32_t adv = nacc >> 5;
-        a0 = adv == 0 ? w0 : (adv == 1 ? w1 : w2);
+        uint32_t t01;
+        asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\tselp.b32 %0, %2, %3, p;\n\t}" : "=r"(t01) : "r"(adv), "r"(w1), "r"(w0));
+        asm("{\n\t.reg .pred p;\n\tsetp.gt.u32 p, %1, 1;\n\tselp.b32 %0, %2, %3, p;\n\t}" : "=r"(a0) : "r"(adv), "r"(w2), "r"(t01));
         wi += adv;
         p += adv * stride;
         nacc &= 31u;
@@ -185,9 +194,9 @@ __device__ __forceinline__ void emit_span(Bits& out, const uint2* __restrict__ l
         const uint2 e = lut[idx];
         const uint32_t nb = (e.y >> 11) & 63u;
         const int pos = 16 * b;
-        const int gap = pos + (int)((e.y >> 17) & 15u) - prev_end;
+        const int gap = pos + (int)((e.y >> 24) & 15u) - prev_end;
         const uint32_t t1 = len_tok[gap];
-        if (nb != kLutLong) {
+        if (!(e.y & kLutLong)) {
             out.put_tok_code(t1, e.x, e.y & 0x7FFu, nb);
         } else {
             // rare: the interior of this byte does not fit a LUT entry -- spell it out mismatch by mismatch
@@ -206,7 +215,7 @@ __device__ __forceinline__ void emit_span(Bits& out, const uint2* __restrict__ l
                 pe = 2 * s + 1;
             }
         }
-        prev_end = pos + (int)((e.y >> 21) & 15u);
+        prev_end = pos + (int)(e.y >> 28);
     }
     {
         const int tail = 4 * nc - 1 - prev_end;
@@ -257,24 +266,47 @@ __device__ __forceinline__ uint32_t mul_tab(const uint32_t* __restrict__ t, uint
            __ldg(&t[768u + (v >> 24)]);
 }
 
-// dynamic shared memory carve-up (words), nthr = blockDim.x
+// dynamic shared memory carve-up, nthr = blockDim.x
 __host__ __device__ inline uint32_t auto_smem_bytes(uint32_t nthr) {
-    return 8192u + 264u * 4u + ((uint32_t)(kAStage + 2) * nthr + 2u * nthr + 24u) * 4u + 20u * nthr + 16u;
+    return 8192u + kATabWords * 4u + ((uint32_t)(kAStage + 2) * nthr + nthr + 24u) * 4u + 20u * nthr + 16u;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src));
 }
 
 __global__ void __launch_bounds__(kFusedMaxThreads, 4) k_auto(const AutoArgs a) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const uint32_t tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31u, wid = tid >> 5;
     uint2* s_lut = reinterpret_cast<uint2*>(smem_raw);
-    uint32_t* s_len = reinterpret_cast<uint32_t*>(s_lut + 1024);
-    uint32_t* s_stage = s_len + 264;
+    uint32_t* s_len = reinterpret_cast<uint32_t*>(s_lut + 1024);   // len_tok | lit | eob | hdr_bits | hdr
+    uint32_t* s_stage = s_len + kATabWords;
     uint32_t* s_last2 = s_stage + (kAStage + 2) * nthr;
-    uint32_t* s_bits = s_last2 + nthr;
-    uint32_t* s_misc = s_bits + nthr;       // [0..7] warp span bits, [8..15] warp prefix bits, [16] crc, [17] overflow, [18..22] lits + eob
+    uint32_t* s_misc = s_last2 + nthr;      // [0..7] warp span bits, [8..9] warp prefix bits, [10] constant crc terms, [16] crc, [17] overflow
     uint8_t* s_mp = reinterpret_cast<uint8_t*>(s_misc + 24);
+    const uint32_t* s_lits = s_len + 264;
+    const uint32_t* s_hdr = s_len + 274;
 
     const FusedDesc d = a.desc[blockIdx.x];
     const AutoTable* __restrict__ tb = a.tables + d.table;
+    {   // code tables of this block's bucket -> shared memory, asynchronously: they are needed after the draws
+        const uint4* src = reinterpret_cast<const uint4*>(tb->lut);
+        uint4* dst = reinterpret_cast<uint4*>(s_lut);
+#pragma unroll
+        for (uint32_t k = 0; k < 8; ++k) {   // nthr >= 64
+            const uint32_t i = tid + k * nthr;
+            if (i < 512u) cp_async16(dst + i, src + i);
+        }
+        const uint4* src2 = reinterpret_cast<const uint4*>(tb->len_tok);
+        uint4* dst2 = reinterpret_cast<uint4*>(s_len);
+#pragma unroll
+        for (uint32_t k = 0; k < 2; ++k) {
+            const uint32_t i = tid + k * nthr;
+            if (i < kATabWords / 4u) cp_async16(dst2 + i, src2 + i);
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+        if (tid == 6) { s_misc[16] = 0; s_misc[17] = 0; }
+    }
     const bool starts_row = d.flags & 1u, ends_row = (d.flags >> 1) & 1u;
     const uint64_t pb = a.nv.pre_off[d.row];
     const uint32_t plen = starts_row ? (uint32_t)(a.nv.pre_off[d.row + 1] - pb) : 0u;
@@ -283,16 +315,6 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 4) k_auto(const AutoArgs a) 
     const uint32_t lead = starts_row ? plen : 1u;
     const uint32_t n = lead + 4u * d.ncells - (ends_row ? 0u : 1u);
     const uint32_t nspans = (d.ncells + 63u) / 64u;
-
-    {   // code tables of this block's bucket -> shared memory
-        const uint4* src = reinterpret_cast<const uint4*>(tb->lut);
-        uint4* dst = reinterpret_cast<uint4*>(s_lut);
-        for (uint32_t i = tid; i < 512u; i += nthr) dst[i] = __ldg(src + i);
-        for (uint32_t i = tid; i < 264u; i += nthr) s_len[i] = __ldg(&tb->len_tok[i]);
-        if (tid < 5) s_misc[18 + tid] = __ldg(&tb->lit[tid]);
-        if (tid == 5) s_misc[23] = __ldg(&tb->eob);
-        if (tid == 6) { s_misc[16] = 0; s_misc[17] = 0; }
-    }
 
     // ---- draw this span's 128 allele bits (replay RNG spec: dnaf_device.cuh)
     const uint32_t cs = d.cell0 + 64u * tid;
@@ -406,6 +428,7 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 4) k_auto(const AutoArgs a) 
         }
     }
     s_last2[tid] = mp[3] >> 30;
+    asm volatile("cp.async.wait_group 0;\n" ::);
     __syncthreads();
     if (lane == 0 && crc) atomicXor(&s_misc[16], crc);
     const uint32_t carry = tid ? s_last2[tid - 1] : (mp[0] & 3u);
@@ -424,8 +447,7 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 4) k_auto(const AutoArgs a) 
         nz = nonzero_bytes(x);
     }
     // ---- pass 1: this span's tokens, staged privately
-    const uint32_t* s_lits = s_misc + 18;
-    const uint32_t eob = s_misc[23];
+    const uint32_t eob = s_len[272];
     const bool worker = nc > 0;
     const bool p_last = worker && 64u * tid + (uint32_t)nc == d.ncells;
     const bool p_end = ends_row && p_last;
@@ -465,19 +487,25 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 4) k_auto(const AutoArgs a) 
     }
     const uint32_t total_pre = plen ? s_misc[8] + s_misc[9] : 0u;   // plen <= 64: two warps
     const uint32_t pre_off = v0 - pre_bits + (wid == 1 ? s_misc[8] : 0u);
-    const uint32_t hdr_bits = __ldg(&tb->hdr_bits);
+    const uint32_t hdr_bits = s_len[273];
     const uint32_t data_bits = hdr_bits + total_pre + total_span;
     const uint32_t payload = (data_bits + 7u) / 8u;
     const uint32_t out_words = (data_bits + 31u) / 32u;
     const bool stored = payload > n + 5u;  // cannot happen with sane tables; keeps BSIZE <= 64 KiB regardless
     uint8_t* blk = a.slots + (uint64_t)d.slot * kSlot + kSlotLead;
-    uint32_t* words = reinterpret_cast<uint32_t*>(blk + 18);  // 4-byte aligned
+    uint32_t* words = reinterpret_cast<uint32_t*>(blk + 18);  // 16-byte aligned
 
     uint32_t out_payload;
     if (!stored) {
-        // zero the words that will be OR-ed into (header words are written, not OR-ed)
+        // header words are written, the words after them zeroed (they are OR-ed into)
         const uint32_t hdr_words = (hdr_bits + 31u) / 32u;
-        for (uint32_t i = tid; i < out_words + 2u; i += nthr) words[i] = i < hdr_words ? __ldg(&tb->hdr[i]) : 0u;
+        const uint32_t hw4 = (hdr_words + 3u) & ~3u;   // <= 64 <= nthr
+        if (tid < hw4) words[tid] = tid < hdr_words ? s_hdr[tid] : 0u;
+        {
+            uint4* w4 = reinterpret_cast<uint4*>(words + hw4);
+            const uint32_t n4 = out_words + 2u > hw4 ? (out_words + 2u - hw4 + 3u) / 4u : 0u;
+            for (uint32_t i = tid; i < n4; i += nthr) w4[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
         __syncthreads();
         const bool overflow = s_misc[17] != 0;
         if (pre_bits) {  // prefix literal: at most 15 bits
@@ -488,24 +516,30 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 4) k_auto(const AutoArgs a) 
         if (worker) {
             const uint32_t dst = hdr_bits + total_pre + span_off;  // first bit of this span in the block
             if (!overflow) {
-                // ---- pass 2 (fast): move the staged bits to their final position
-                const uint32_t nb = my_bits;
+                // ---- pass 2 (fast): move the staged bits to their final position; only the first and the last
+                // destination word can be shared with a neighbour
                 const uint32_t sh = dst & 31u;
-                const uint32_t nsrc = (nb + 31u) / 32u;
-                const uint32_t ndst = (sh + nb + 31u) / 32u;
+                const uint32_t nsrc = (my_bits + 31u) / 32u;
+                const uint32_t ndst = (sh + my_bits + 31u) / 32u;
                 uint32_t* o = words + (dst >> 5);
-                uint32_t prev = 0;
-                for (uint32_t k = 0; k < ndst; ++k) {
-                    const uint32_t cur = k < nsrc ? s_stage[k * nthr + tid] : 0u;
-                    const uint32_t v = __funnelshift_l(prev, cur, sh);  // (cur:prev) << sh, upper word
-                    if (k == 0 || k == ndst - 1) atomicOr(&o[k], v);
-                    else o[k] = v;
+                const uint32_t* sp = s_stage + tid;
+                uint32_t prev = my_bits ? sp[0] : 0u;
+                atomicOr(&o[0], prev << sh);
+                uint32_t k = 1;
+                for (; k + 1u < ndst; ++k) {
+                    const uint32_t cur = sp[k * nthr];
+                    o[k] = __funnelshift_l(prev, cur, sh);
                     prev = cur;
                 }
+                if (k < ndst) {
+                    const uint32_t cur = k < nsrc ? sp[k * nthr] : 0u;
+                    atomicOr(&o[k], __funnelshift_l(prev, cur, sh));
+                }
             } else {
-                // ---- pass 2 (slow): emit straight into the output words
+                // ---- pass 2 (slow): some span overflowed its staging words -- emit straight into the output words
                 AEmit em{words, dst};
-                emit_span(em, s_lut, s_len, s_lits, eob, s_mp + 20u * tid, nz, mp[0], mlast_bit, tid == 0, starts_row, nc, p_end, p_last);
+                ATokSink<AEmit> ts{em, s_len, s_lits, eob};
+                span_tokens_ref(mp, carry, tid == 0, starts_row, nc, p_end, p_last, ts);
             }
         }
         out_payload = payload;

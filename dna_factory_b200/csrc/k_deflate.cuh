@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(256, 1) k_bgzf_generic(const uint8_t* __restri
     const bool stored = payload > n + 5u || payload > kSlot - 26u;
 
     const uint32_t slot_no = slot_idx ? slot_idx[blockIdx.x] : blockIdx.x;
-    uint8_t* slot = slots + (uint64_t)slot_no * kSlot + 2;  // blocks start at slot + 2 (see k_fused.cuh)
+    uint8_t* slot = slots + (uint64_t)slot_no * kSlot + kSlotLead;  // see dnaf_device.cuh
     uint32_t out_payload;
     if (!stored) {
         // -- pass 3: emit
@@ -419,10 +419,10 @@ __global__ void __launch_bounds__(1024) k_scan_sizes(const uint32_t* __restrict_
 __global__ void __launch_bounds__(256) k_compact(const uint8_t* __restrict__ slots, uint32_t slot_stride,
                                                 const uint32_t* __restrict__ sizes, const uint64_t* __restrict__ offsets,
                                                 uint8_t* __restrict__ out) {
-    const uint8_t* src = slots + (uint64_t)blockIdx.x * slot_stride + 2;
+    const uint8_t* src = slots + (uint64_t)blockIdx.x * slot_stride + kSlotLead;
     uint8_t* dst = out + offsets[blockIdx.x];
     const uint32_t n = sizes[blockIdx.x];
-    // 16-byte stores to the destination; the source (slot + 2) is read as 16-bit units
+    // 16-byte stores to the destination; the source (slot + kSlotLead) is read as 16-bit units
     const uint32_t head = min(n, (uint32_t)((16u - (reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u));
     for (uint32_t i = threadIdx.x; i < head; i += blockDim.x) dst[i] = src[i];
     const uint32_t body = (n - head) / 16u;

@@ -267,8 +267,6 @@ struct FusedArgs {
     uint32_t* crcs;
 };
 
-// Slot layout: the BGZF block starts at slot + 2, so that its deflate payload (slot + 20) is word aligned.
-constexpr uint32_t kSlotLead = 2;
 
 // One CTA per BGZF block.  Thread t draws span t (64 samples) and owns prefix byte t; the tokenisation of
 // the spans is then dealt out by mismatch count (a counting sort inside the CTA), so that the 32 lanes of

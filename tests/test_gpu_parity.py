@@ -124,6 +124,35 @@ def test_fused_kernel_vs_oracle_and_generic(native, n, s, seed):
     assert st_f["bgzf_bytes"] < 1.10 * st_p["bgzf_bytes"] + 4096
 
 
+@pytest.mark.parametrize("n,stride", [(8192, 2), (8200, 3), (20000, 7), (12345, 1)])
+def test_auto_kernel_dense_overrides_on_rare_rows(native, n, stride):
+    """Forced-minor cells (pop_factory.py:495-499) in patterns the rare-MAF code tables never expect: byte patterns
+    whose tokens do not fit a LUT entry and spans that overflow their staging words must still decode exactly."""
+    from oracle import oracle
+    from tests.cases import Snp, Sample
+    from types import SimpleNamespace
+    snps = [Snp(id=i + 1, chromosome='1', position=1000 * (i + 1), tuples=[("A", 1 - maf), ("C", 1.0)])
+            for i, maf in enumerate([0.005, 0.01, 0.02, 0.25, 0.495, 0.005])]
+    samples = []
+    for i in range(n):
+        ctl = i < n // 3
+        d = None
+        if not ctl:
+            # every `stride`-th case carries every SNP; the last row only on a short burst of cases
+            d = {s.id: 0.5 for s in snps[:5]} if (i % stride == 0) else {}
+            if n // 2 <= i < n // 2 + 70:
+                d[6] = 0.5
+        samples.append(Sample(family_id=i + 1, person_id=100001 + i, father_id=0, mother_id=0, sex=1 + (i & 1),
+                              is_control=ctl, deleterious_snps=d))
+    case = SimpleNamespace(name="dense", seed=0xD15EA5E, row_begin=0, samples=samples, snps=snps, text=None)
+    want, _ = oracle.rows(case.samples, case.snps, case.seed, 0, n_threads=4)
+    eng = _engine(native, case)
+    blob, st = eng.generate(0, len(snps), case.seed, level=2)
+    assert st["ms_fused"] > 0
+    text, blocks, _ = oracle.bgzf_decompress(blob)
+    assert text == want and blocks == st["bgzf_blocks"]
+
+
 @pytest.mark.parametrize("n,s,seed,odds", [(8192, 16, 41, 0.5), (8193, 16, 42, 0.5), (9000, 12, 43, 0.0),
                                            (9000, 12, 44, 1.0), (20000, 20, 45, 0.5), (40000, 8, 46, 0.3)])
 def test_fused_text_kernel_all_classes(native, n, s, seed, odds):
