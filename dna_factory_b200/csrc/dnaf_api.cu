@@ -44,7 +44,7 @@ struct DevBuf {
     cudaError_t reserve(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
         release();
-        const size_t want = bytes + bytes / 8 + 256;
+        const size_t want = std::max<size_t>(bytes + bytes / 2, 64 << 10);   // geometric: sizes settle after a few passes
         cudaError_t e = cudaMalloc(&p, want);
         if (e == cudaSuccess) cap = want;
         return e;
@@ -65,7 +65,7 @@ struct PinnedBuf {
     cudaError_t reserve(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
         release();
-        const size_t want = bytes + bytes / 8 + 256;
+        const size_t want = std::max<size_t>(bytes + bytes / 2, 64 << 10);
         cudaError_t e = cudaMallocHost(&p, want);
         if (e == cudaSuccess) cap = want;
         return e;
@@ -129,6 +129,7 @@ struct dnaf_ctx {
     cudaEvent_t ev[8] = {};
     cudaStream_t side = nullptr;           // k_fused_text runs here, concurrently with k_fused_auto
     cudaStream_t copy = nullptr;           // D2H of pass i overlaps the kernels of pass i+1
+    cudaStream_t tot = nullptr;            // 16-byte totals read-backs (never queued behind a data copy)
     struct OutBuf {                        // what must outlive a pass while the next one runs
         DevBuf d_out, d_totals;
         PinnedBuf h_totals, h_out, h_stage;  // h_stage: descriptor uploads of the pass (truly asynchronous H2D)
@@ -138,7 +139,9 @@ struct dnaf_ctx {
         uint32_t nb = 0;
         uint64_t rows = 0, text = 0;
         bool gen = false, fused = false, generic_blocks = false;
-    } ob[2];
+        int copy_mode = 0;                   // 0 nothing in flight, 1 DMA into the caller's pinned buffer, 2 via h_out
+        uint64_t copy_bytes = 0;
+    } ob[3];
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool attr_done = false;
 
@@ -170,6 +173,11 @@ struct dnaf_ctx {
     DevBuf d_atables, d_etab2, d_mtab, d_mtail, d_mpre, d_xinit, d_pre_crc;
     std::map<std::pair<uint64_t, uint64_t>, AutoTable> atable_cache;
     std::vector<uint32_t> h_mtail, h_mpre;
+    DevBuf d_pfx_state;
+    PinnedBuf h_present;                   // byte values seen in the row prefixes (written by k_prefix_crc)
+    uint32_t present_sticky[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // prefix byte values seen so far (a superset keeps table keys stable)
+    std::vector<uint8_t> need_sticky;      // (bucket, variant) tables ever needed: the uploaded set only grows
+    std::vector<uint32_t> bk_key; std::vector<int> bk_val;   // direct-mapped cache in front of bucket_of
     bool seg_tabs_dirty = false;
     std::vector<uint8_t> h_pfx_tab;        // per row: prefix ends with '\t' (k_auto's first match may reach into it)
     std::vector<XSpan> h_xspans;
@@ -202,6 +210,13 @@ int fail(dnaf_ctx* c, int code, const char* fmt, ...) {
             return fail((c), e__ == cudaErrorMemoryAllocation ? DNAF_E_NOMEM : DNAF_E_CUDA, "%s: %s", #call, \
                         cudaGetErrorString(e__));                                                     \
     } while (0)
+
+static bool g_trace = getenv("DNAF_TRACE") != nullptr;
+static std::chrono::steady_clock::time_point g_t0;
+static void trace(const char* what, int pass) {
+    if (!g_trace) return;
+    fprintf(stderr, "[dnaf] %8.3f ms  %s %d\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - g_t0).count(), what, pass);
+}
 
 template <class T>
 int upload(dnaf_ctx* c, DevBuf& b, const T* src, size_t count, bool sync = true) {
@@ -238,6 +253,7 @@ int ensure_tables(dnaf_ctx* c);
 int ensure_layout(dnaf_ctx* c) {
     if (!c->have_samples || !c->have_snps) return fail(c, DNAF_E_ARG, "set_samples and set_snps must be called first");
     if (c->layout_ok) return DNAF_OK;
+    if (g_trace) { g_t0 = std::chrono::steady_clock::now(); trace("ensure_layout begins", 0); }
     c->h_row_off.resize(c->S + 1);
     uint64_t acc = 0;
     for (uint64_t r = 0; r < c->S; ++r) {
@@ -245,8 +261,10 @@ int ensure_layout(dnaf_ctx* c) {
         acc += (uint64_t)c->h_plen[r] + c->body[c->h_cls[r]];
     }
     c->h_row_off[c->S] = acc;
+    trace("row offsets summed", 0);
     int rc = upload(c, c->d_row_off, c->h_row_off.data(), c->S + 1);
     if (rc) return rc;
+    trace("row offsets uploaded", 0);
     build_segments(c);
     if (c->seg_tabs_dirty) {
         rc = upload(c, c->d_mtail, c->h_mtail.data(), c->h_mtail.size());
@@ -256,6 +274,7 @@ int ensure_layout(dnaf_ctx* c) {
     }
     rc = ensure_tables(c);
     if (rc) return rc;
+    trace("tables ensured", 0);
     c->layout_ok = true;
     return DNAF_OK;
 }
@@ -273,7 +292,7 @@ uint32_t raw_crc(const uint8_t* p, size_t n, const uint32_t* tab) {
 constexpr int kVariants = 12;  // tables per MAF bucket: auto+prefix, auto, (class x {prefix, no prefix}) for k_fused_text, X+prefix, X for k_fused_x
 
 // Called from set_snps: bucket every row by its first threshold, remember which prefix bytes occur.
-int prepare_buckets(dnaf_ctx* c, const uint8_t* kk, const uint32_t* thr, const uint8_t* prefix, const uint64_t* pre_off) {
+int prepare_buckets(dnaf_ctx* c, const uint8_t* kk, const uint32_t* thr) {
     c->h_bucket.assign(c->S, 0);
     if (c->S == 0) return DNAF_OK;
     // bucket key: the first threshold (minor-allele probability = 1 - (T+1)/2^32), coarsened (shift) if a
@@ -283,9 +302,18 @@ int prepare_buckets(dnaf_ctx* c, const uint8_t* kk, const uint32_t* thr, const u
         bool ok = true;
         uint32_t last_key = 0;
         int last_bucket = -1;
+        c->bk_key.assign(1024, 0);
+        c->bk_val.assign(1024, -1);
         for (uint64_t r = 0; r < c->S; ++r) {
             const uint32_t key = (kk[r] >= 2 ? thr[r * 4] : 0xFFFFFFFFu) >> c->bucket_shift;
             if (last_bucket < 0 || key != last_key) {
+                const uint32_t h = (key * 2654435761u) >> 22;
+                if (c->bk_val[h] >= 0 && c->bk_key[h] == key) {
+                    last_key = key;
+                    last_bucket = c->bk_val[h];
+                    c->h_bucket[r] = (uint16_t)last_bucket;
+                    continue;
+                }
                 auto it = c->bucket_of.find(key);
                 if (it == c->bucket_of.end()) {
                     if (c->bucket_of.size() >= 512) { ok = false; break; }
@@ -297,6 +325,8 @@ int prepare_buckets(dnaf_ctx* c, const uint8_t* kk, const uint32_t* thr, const u
                 }
                 last_key = key;
                 last_bucket = it->second;
+                c->bk_key[h] = key;
+                c->bk_val[h] = last_bucket;
             }
             c->h_bucket[r] = (uint16_t)last_bucket;
         }
@@ -305,18 +335,20 @@ int prepare_buckets(dnaf_ctx* c, const uint8_t* kk, const uint32_t* thr, const u
         c->bucket_of.clear();
         c->bucket_p.clear();
         c->tables_sig.clear();
-    }
-    // prefix byte model (x16 fixed point per row): which bytes occur, weighted by kind -- deliberately not the
-    // exact counts, so that tables can be cached across set_snps calls with similar prefixes
-    c->ph.assign(256, 0);
-    const uint64_t total = pre_off[c->S];
-    for (uint64_t i = 0; i < total; ++i) c->ph[prefix[i]] = 1;
-    c->ph_hash = 1469598103934665603ull;
-    for (int b = 0; b < 256; ++b) {
-        if (c->ph[b]) c->ph[b] = b == '\t' ? 144 : ((b >= '0' && b <= '9') ? 24 : 16);
-        c->ph_hash = (c->ph_hash ^ c->ph[b]) * 1099511628211ull;
+        c->need_sticky.clear();
     }
     return DNAF_OK;
+}
+
+// prefix byte model (x16 fixed point per row): which bytes occur (from k_prefix_crc), weighted by kind --
+// deliberately not the exact counts, so that tables can be cached across set_snps calls with similar prefixes
+void prefix_model(dnaf_ctx* c, const uint32_t* present) {
+    c->ph.assign(256, 0);
+    c->ph_hash = 1469598103934665603ull;
+    for (int b = 0; b < 256; ++b) {
+        if ((present[b >> 5] >> (b & 31)) & 1u) c->ph[b] = b == '\t' ? 144 : ((b >= '0' && b <= '9') ? 24 : 16);
+        c->ph_hash = (c->ph_hash ^ c->ph[b]) * 1099511628211ull;
+    }
 }
 
 // Called from ensure_layout (samples and SNPs known): static Huffman tables for every (bucket, variant) in use.
@@ -334,6 +366,19 @@ int ensure_tables(dnaf_ctx* c) {
         } else {
             need[b * kVariants + 2 + 2 * c->h_cls[r]] = need[b * kVariants + 3 + 2 * c->h_cls[r]] = 1;
         }
+    }
+    // Tables stay once they have been needed, and a bucket gets every variant any bucket has needed: successive SNP
+    // batches differ in which buckets their (few) X / Y rows hit, and the uploaded set must settle quickly.
+    if (c->need_sticky.size() < need.size()) c->need_sticky.resize(need.size(), 0);
+    {
+        uint8_t var_seen[kVariants] = {0};
+        std::vector<uint8_t> bucket_seen(nb, 0);
+        for (int b = 0; b < nb; ++b)
+            for (int v = 0; v < kVariants; ++v)
+                if (need[b * kVariants + v] | c->need_sticky[b * kVariants + v]) var_seen[v] = bucket_seen[b] = 1;
+        for (int b = 0; b < nb; ++b)
+            for (int v = 0; v < kVariants; ++v)
+                need[b * kVariants + v] = c->need_sticky[b * kVariants + v] = bucket_seen[b] && var_seen[v];
     }
     std::vector<uint64_t> sig;
     sig.reserve(need.size() + 2);
@@ -711,12 +756,14 @@ int reserve_stage(dnaf_ctx* c, dnaf_ctx::OutBuf& B) {
     return DNAF_OK;
 }
 
-int reserve_outputs(dnaf_ctx* c, dnaf_ctx::OutBuf& B, uint32_t nb) {
+int reserve_outputs(dnaf_ctx* c, dnaf_ctx::OutBuf& B, uint32_t nb_exact) {
+    // whole multiples of 2048 blocks: passes of a job differ a little in block count, buffers must not be
+    // re-allocated (cudaMalloc synchronises the device) every time one is a few blocks larger than the last
+    const uint32_t nb = nb_exact > 256u ? (nb_exact + 2047u) / 2048u * 2048u : nb_exact;
     CU(c, c->d_slots.reserve((size_t)nb * kSlot));
     CU(c, c->d_sizes.reserve(nb * sizeof(uint32_t)));
     CU(c, c->d_crcs.reserve(nb * sizeof(uint32_t)));
-    CU(c, c->d_offsets.reserve(nb * sizeof(uint64_t)));
-    CU(c, B.d_totals.reserve(2 * sizeof(uint64_t)));
+    CU(c, B.d_totals.reserve((4 + (size_t)(nb + kTile - 1u) / kTile) * sizeof(uint64_t)));   // scan state of k_scan_compact
     CU(c, B.d_out.reserve((size_t)nb * kSlot));
     CU(c, B.h_totals.reserve(2 * sizeof(uint64_t)));
     if (!c->attr_done) {
@@ -746,38 +793,32 @@ int launch_generic(dnaf_ctx* c, dnaf_stats* st) {
 int close_pass(dnaf_ctx* c, dnaf_ctx::OutBuf& B, uint32_t nb, dnaf_stats* st) {
     B.nb = nb;
     if (nb) {
-        k_scan_sizes<<<1, 1024, 0, c->stream>>>(c->d_sizes.as<uint32_t>(), nb, c->d_offsets.as<uint64_t>(),
-                                                c->d_crcs.as<uint32_t>(), B.d_totals.as<uint64_t>());
-        k_compact<<<nb, 256, 0, c->stream>>>(c->d_slots.as<uint8_t>(), kSlot, c->d_sizes.as<uint32_t>(),
-                                             c->d_offsets.as<uint64_t>(), B.d_out.as<uint8_t>());
-        if (st) st->kernel_launches += 2;
+        const uint32_t ntiles = (nb + kTile - 1u) / kTile;
+        CU(c, cudaMemsetAsync(B.d_totals.p, 0, (4 + (size_t)ntiles) * sizeof(uint64_t), c->stream));
+        k_scan_compact<<<ntiles, 256, 0, c->stream>>>(c->d_slots.as<uint8_t>(), kSlot, c->d_sizes.as<uint32_t>(),
+                                                      c->d_crcs.as<uint32_t>(), nb,
+                                                      reinterpret_cast<unsigned long long*>(B.d_totals.p),
+                                                      reinterpret_cast<unsigned long long*>(B.h_totals.p), B.d_out.as<uint8_t>());
+        if (st) st->kernel_launches += 1;
     }
     CU(c, cudaEventRecord(B.ev[5], c->stream));
     CU(c, cudaGetLastError());
     return DNAF_OK;
 }
 
-// Queue the 16-byte totals read-back of a closed pass on the copy stream.  Called AFTER the previous pass
-// has been retired: the copy stream is FIFO, so queuing this wait-for-kernels first would hold that
-// pass's data copy back until the new kernels are done.
-int queue_totals(dnaf_ctx* c, dnaf_ctx::OutBuf& B) {
-    if (B.nb) {
-        CU(c, cudaStreamWaitEvent(c->copy, B.ev[5], 0));
-        CU(c, cudaMemcpyAsync(B.h_totals.p, B.d_totals.p, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->copy));
-    }
-    CU(c, cudaEventRecord(B.ev_totals, c->copy));
-    return DNAF_OK;
-}
+int queue_totals(dnaf_ctx*, dnaf_ctx::OutBuf&) { return DNAF_OK; }   // k_scan_compact stores the totals to host memory itself
 
-// wait for a closed pass, move its bytes to the sink (directly into a pinned caller buffer when possible)
-int retire_pass(dnaf_ctx* c, dnaf_ctx::OutBuf& B, Sink& sink, dnaf_stats* st) {
+// A closed pass: wait for its kernels and totals, account it, and START moving its bytes to the host (straight
+// into a page-locked caller buffer when there is one).  finish_copy() completes the move.
+int start_copy(dnaf_ctx* c, dnaf_ctx::OutBuf& B, Sink& sink, dnaf_stats* st) {
+    trace("start_copy: wait kernels", (int)B.nb);
     CU(c, cudaEventSynchronize(B.ev[5]));
-    CU(c, cudaEventSynchronize(B.ev_totals));
-    const uint64_t bytes = B.nb ? B.h_totals.as<uint64_t>()[0] : 0;
+    trace("start_copy: kernels done", (int)B.nb);
+    const uint64_t bytes = B.nb ? *reinterpret_cast<volatile uint64_t*>(B.h_totals.p) : 0;
     if (st) {
         st->bgzf_bytes += bytes;
         st->bgzf_blocks += B.nb;
-        if (B.nb) st->crc_xor ^= (uint32_t)B.h_totals.as<uint64_t>()[1];
+        if (B.nb) st->crc_xor ^= (uint32_t)reinterpret_cast<volatile uint64_t*>(B.h_totals.p)[1];
         float t01 = 0, t12 = 0, t23 = 0, t34 = 0, t45 = 0, t05 = 0;
         cudaEventElapsedTime(&t01, B.ev[0], B.ev[1]);
         cudaEventElapsedTime(&t12, B.ev[1], B.ev[2]);
@@ -795,6 +836,8 @@ int retire_pass(dnaf_ctx* c, dnaf_ctx::OutBuf& B, Sink& sink, dnaf_stats* st) {
         st->rows += B.rows;
         st->text_bytes += B.text;
     }
+    B.copy_mode = 0;
+    B.copy_bytes = bytes;
     if (sink.device_only || !bytes) {
         sink.used += bytes;
         return DNAF_OK;
@@ -804,15 +847,26 @@ int retire_pass(dnaf_ctx* c, dnaf_ctx::OutBuf& B, Sink& sink, dnaf_stats* st) {
             return fail(c, DNAF_E_SPACE, "output buffer too small: need more than %llu bytes", (unsigned long long)sink.cap);
         CU(c, cudaMemcpyAsync(sink.buf + sink.used, B.d_out.p, bytes, cudaMemcpyDeviceToHost, c->copy));
         CU(c, cudaEventRecord(B.ev_copied, c->copy));
-        CU(c, cudaEventSynchronize(B.ev_copied));
         sink.used += bytes;
+        B.copy_mode = 1;
         return DNAF_OK;
     }
     CU(c, B.h_out.reserve(bytes));
     CU(c, cudaMemcpyAsync(B.h_out.p, B.d_out.p, bytes, cudaMemcpyDeviceToHost, c->copy));
     CU(c, cudaEventRecord(B.ev_copied, c->copy));
+    B.copy_mode = 2;
+    return DNAF_OK;
+}
+
+int finish_copy(dnaf_ctx* c, dnaf_ctx::OutBuf& B, Sink& sink) {
+    const int mode = B.copy_mode;
+    B.copy_mode = 0;
+    if (!mode) return DNAF_OK;
+    trace("finish_copy: wait", (int)B.nb);
     CU(c, cudaEventSynchronize(B.ev_copied));
-    return deliver(c, sink, B.h_out.as<uint8_t>(), bytes);
+    trace("finish_copy: done", (int)B.nb);
+    if (mode == 2) return deliver(c, sink, B.h_out.as<uint8_t>(), B.copy_bytes);
+    return DNAF_OK;
 }
 
 // sample (+ overrides) `rows` rows into the plane buffers; row list optional (d_grow), overrides as local pairs
@@ -897,8 +951,16 @@ int generate_impl(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t se
         else cudaGetLastError();
     }
     uint64_t r0 = row_begin;
-    int cur = 0, pending = -1;
+    // Three output buffers in rotation.  Pass i is launched as soon as the copy of pass i-3 (same buffer) has landed,
+    // i.e. without waiting for anything recent, so the GPU runs ahead; then the copy of pass i-1 is queued behind
+    // the copy of pass i-2 that is still in flight, so the copy engine never waits for the host either.
+    for (auto& b : c->ob) b.copy_mode = 0;
+    int npass = 0;
+    if (g_trace) { g_t0 = std::chrono::steady_clock::now(); trace("generate begins", 0); }
     while (r0 < row_end) {
+        const int cur = npass % 3;
+        rc = finish_copy(c, c->ob[cur], sink);
+        if (rc) return rc;
         const uint64_t r1 = next_chunk_end(c, r0, row_end, c->chunk_bytes);
         dnaf_ctx::OutBuf& B = c->ob[cur];
         const auto t_plan0 = std::chrono::steady_clock::now();
@@ -927,9 +989,18 @@ int generate_impl(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t se
         rc = launch_generic(c, &local);
         if (rc) return rc;
         CU(c, cudaEventRecord(B.ev[3], c->stream));
+        // descriptors of the three fused kernels go up first; the few, long blocks of k_fused_text / k_fused_x then start
+        // on the high-priority side stream and k_auto fills the rest of the chip from the main stream
+        if (!c->tplan.empty()) rc = upload_async(c, c->d_tdesc, c->tplan);
+        if (!rc && !c->xplan.empty()) rc = upload_async(c, c->d_xdesc, c->xplan);
+        if (!rc && !c->fplan.empty()) rc = upload_async(c, c->d_fdesc, c->fplan);
+        if (rc) return rc;
+        const bool side_work = !c->tplan.empty() || !c->xplan.empty();
+        if (side_work) {
+            CU(c, cudaEventRecord(c->ev_fork, c->stream));
+            CU(c, cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+        }
         if (!c->tplan.empty()) {
-            rc = upload_async(c, c->d_tdesc, c->tplan);
-            if (rc) return rc;
             if (!c->text_attr_done) {
                 CU(c, cudaFuncSetAttribute(k_fused_text, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TextSmem)));
                 c->text_attr_done = true;
@@ -949,17 +1020,34 @@ int generate_impl(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t se
             ta.slots = c->d_slots.as<uint8_t>();
             ta.sizes = c->d_sizes.as<uint32_t>();
             ta.crcs = c->d_crcs.as<uint32_t>();
-            // few, long blocks: start them first on the side stream so that k_fused_auto fills the rest of the chip
-            CU(c, cudaEventRecord(c->ev_fork, c->stream));
-            CU(c, cudaStreamWaitEvent(c->side, c->ev_fork, 0));
             k_fused_text<<<(uint32_t)c->tplan.size(), c->text_threads, sizeof(TextSmem), c->side>>>(ta);
-            CU(c, cudaEventRecord(c->ev_join, c->side));
             local.kernel_launches += 1;
             CU(c, cudaGetLastError());
         }
+        if (!c->xplan.empty()) {
+            XArgs xa;
+            xa.f.sv = sample_view(c);
+            xa.f.nv = snp_view(c);
+            xa.f.desc = c->d_xdesc.as<FusedDesc>();
+            xa.f.tables = c->d_ftables.as<FusedTable>();
+            xa.f.etab = c->d_etab.as<uint32_t>();
+            xa.f.crctab = c->d_crctab.as<uint32_t>();
+            xa.f.xpow8 = c->d_xpow8.as<uint32_t>();
+            xa.f.orow = c->d_orow.as<uint64_t>();
+            xa.f.osamp = c->d_osamp.as<uint32_t>();
+            xa.f.row_base = c->row_base;
+            xa.f.k0 = (uint32_t)seed;
+            xa.f.k1 = (uint32_t)(seed >> 32);
+            xa.f.slots = c->d_slots.as<uint8_t>();
+            xa.f.sizes = c->d_sizes.as<uint32_t>();
+            xa.f.crcs = c->d_crcs.as<uint32_t>();
+            xa.xspans = c->d_xspans.as<XSpan>();
+            k_fused_x<<<(uint32_t)c->xplan.size(), c->fused_threads, 0, c->side>>>(xa);
+            local.kernel_launches += 1;
+            CU(c, cudaGetLastError());
+        }
+        if (side_work) CU(c, cudaEventRecord(c->ev_join, c->side));
         if (!c->fplan.empty()) {
-            rc = upload_async(c, c->d_fdesc, c->fplan);
-            if (rc) return rc;
             AutoArgs fa;
             fa.sv = sample_view(c);
             fa.nv = snp_view(c);
@@ -984,31 +1072,7 @@ int generate_impl(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t se
             local.kernel_launches += 1;
             CU(c, cudaGetLastError());
         }
-        if (!c->xplan.empty()) {
-            rc = upload_async(c, c->d_xdesc, c->xplan);
-            if (rc) return rc;
-            XArgs xa;
-            xa.f.sv = sample_view(c);
-            xa.f.nv = snp_view(c);
-            xa.f.desc = c->d_xdesc.as<FusedDesc>();
-            xa.f.tables = c->d_ftables.as<FusedTable>();
-            xa.f.etab = c->d_etab.as<uint32_t>();
-            xa.f.crctab = c->d_crctab.as<uint32_t>();
-            xa.f.xpow8 = c->d_xpow8.as<uint32_t>();
-            xa.f.orow = c->d_orow.as<uint64_t>();
-            xa.f.osamp = c->d_osamp.as<uint32_t>();
-            xa.f.row_base = c->row_base;
-            xa.f.k0 = (uint32_t)seed;
-            xa.f.k1 = (uint32_t)(seed >> 32);
-            xa.f.slots = c->d_slots.as<uint8_t>();
-            xa.f.sizes = c->d_sizes.as<uint32_t>();
-            xa.f.crcs = c->d_crcs.as<uint32_t>();
-            xa.xspans = c->d_xspans.as<XSpan>();
-            k_fused_x<<<(uint32_t)c->xplan.size(), c->fused_threads, 0, c->stream>>>(xa);
-            local.kernel_launches += 1;
-            CU(c, cudaGetLastError());
-        }
-        if (!c->tplan.empty()) CU(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+        if (side_work) CU(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
         CU(c, cudaEventRecord(B.ev[4], c->stream));
         B.rows = r1 - r0;
         B.text = c->h_row_off[r1] - c->h_row_off[r0];
@@ -1017,25 +1081,28 @@ int generate_impl(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t se
         B.fused = !c->fplan.empty() || !c->tplan.empty() || !c->xplan.empty();
         rc = close_pass(c, B, c->pass_blocks, &local);
         if (rc) return rc;
-        if (getenv("DNAF_TRACE")) {
+        if (g_trace) {
             const auto t_l = std::chrono::steady_clock::now();
             fprintf(stderr, "[dnaf] pass rows %llu: plan %.0f us, launch %.0f us\n", (unsigned long long)(r1 - r0),
                     std::chrono::duration<double, std::micro>(t_plan1 - t_plan0).count(),
                     std::chrono::duration<double, std::micro>(t_l - t_plan1).count());
-        }
-        // the previous pass is copied out while this one computes
-        if (pending >= 0) {
-            rc = retire_pass(c, c->ob[pending], sink, &local);
-            if (rc) return rc;
+            trace("launched pass", npass);
         }
         rc = queue_totals(c, B);
         if (rc) return rc;
-        pending = cur;
-        cur ^= 1;
+        if (npass >= 1) {
+            rc = start_copy(c, c->ob[(npass - 1) % 3], sink, &local);
+            if (rc) return rc;
+        }
+        ++npass;
         r0 = r1;
     }
-    if (pending >= 0) {
-        rc = retire_pass(c, c->ob[pending], sink, &local);
+    if (npass >= 1) {
+        rc = start_copy(c, c->ob[(npass - 1) % 3], sink, &local);
+        if (rc) return rc;
+    }
+    for (int k = std::max(0, npass - 3); k < npass; ++k) {   // in pass order: staged sinks are delivered here
+        rc = finish_copy(c, c->ob[k % 3], sink);
         if (rc) return rc;
     }
     local.calls = local.rows * c->n;
@@ -1079,6 +1146,7 @@ int dnaf_create(int device_ordinal, dnaf_ctx** out) {
         if ((e = cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, hi)) != cudaSuccess) return bail("cudaStreamCreate", e);
     }
     if ((e = cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    if ((e = cudaStreamCreateWithFlags(&c->tot, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     for (auto& b : c->ob) {
         for (auto& ev : b.ev)
             if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
@@ -1115,6 +1183,7 @@ void dnaf_destroy(dnaf_ctx* c) {
         if (ev) cudaEventDestroy(ev);
     if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
     if (c->copy) { cudaStreamSynchronize(c->copy); cudaStreamDestroy(c->copy); }
+    if (c->tot) { cudaStreamSynchronize(c->tot); cudaStreamDestroy(c->tot); }
     for (auto& b : c->ob) {
         for (auto& ev : b.ev)
             if (ev) cudaEventDestroy(ev);
@@ -1208,6 +1277,7 @@ int dnaf_set_snps(dnaf_ctx* c, uint64_t S, const uint8_t* cls, const uint8_t* k,
     if (!c) return DNAF_E_ARG;
     if (S && (!cls || !k || !thr || !prefix || !pre_off)) return fail(c, DNAF_E_ARG, "NULL SNP array");
     CU(c, cudaSetDevice(c->dev));
+    if (g_trace) { g_t0 = std::chrono::steady_clock::now(); trace("set_snps begins", 0); }
     bool multi = false;
     for (uint64_t r = 0; r < S; ++r) {
         if (cls[r] > kMT) return fail(c, DNAF_E_ARG, "row %llu: bad chromosome class %u", (unsigned long long)r, cls[r]);
@@ -1231,12 +1301,13 @@ int dnaf_set_snps(dnaf_ctx* c, uint64_t S, const uint8_t* cls, const uint8_t* k,
         c->h_plen[r] = (uint32_t)(pre_off[r + 1] - pre_off[r]);
         c->h_pfx_tab[r] = c->h_plen[r] && prefix[pre_off[r + 1] - 1] == '\t';
     }
+    trace("validated, host copies made", 0);
     // pageable sources: each copy returns once the data is staged, one synchronise covers them all
     int rc = upload(c, c->d_cls, cls, S, false);
     if (!rc) rc = upload(c, c->d_k, k, S, false);
     if (!rc) rc = upload(c, c->d_thr, thr, S * 4, false);
     if (!rc) rc = upload(c, c->d_prefix, prefix, S ? pre_off[S] : 0, false);
-    if (!rc) rc = upload(c, c->d_pre_off, pre_off, S + 1);
+    if (!rc) rc = upload(c, c->d_pre_off, pre_off, S + 1, S == 0);
     if (rc) return rc;
     if (S == 0) {
         const uint64_t zero = 0;
@@ -1244,14 +1315,24 @@ int dnaf_set_snps(dnaf_ctx* c, uint64_t S, const uint8_t* cls, const uint8_t* k,
         if (rc) return rc;
     } else {   // per-row linear CRC of the prefix (k_auto adds it to its blocks' checksums with four lookups)
         CU(c, c->d_pre_crc.reserve(S * sizeof(uint32_t)));
+        CU(c, c->d_pfx_state.reserve(16 * sizeof(uint32_t)));
+        CU(c, c->h_present.reserve(8 * sizeof(uint32_t)));
+        CU(c, cudaMemsetAsync(c->d_pfx_state.p, 0, 16 * sizeof(uint32_t), c->stream));
         k_prefix_crc<<<(uint32_t)((S + 255) / 256), 256, 0, c->stream>>>(c->d_prefix.as<uint8_t>(), c->d_pre_off.as<uint64_t>(), S,
-                                                                       c->d_crctab.as<uint32_t>(), c->d_pre_crc.as<uint32_t>());
+                                                                       c->d_crctab.as<uint32_t>(), c->d_pre_crc.as<uint32_t>(),
+                                                                       c->d_pfx_state.as<uint32_t>(), c->h_present.as<uint32_t>());
         CU(c, cudaGetLastError());
+        CU(c, cudaStreamSynchronize(c->stream));   // the uploads above and the kernel
+        uint32_t present[8];
+        for (int w = 0; w < 8; ++w) present[w] = c->present_sticky[w] |= reinterpret_cast<volatile uint32_t*>(c->h_present.p)[w];
+        prefix_model(c, present);
     }
+    trace("uploaded", 0);
     c->have_snps = true;
     c->layout_ok = false;
-    rc = prepare_buckets(c, k, thr, prefix, pre_off);
+    rc = prepare_buckets(c, k, thr);
     if (rc) return rc;
+    trace("buckets prepared", 0);
     return DNAF_OK;
 }
 
@@ -1421,7 +1502,8 @@ int dnaf_bgzf_compress(dnaf_ctx* c, const uint8_t* text, uint64_t n, int level, 
         rc = launch_generic(c, &local);
         if (!rc) rc = close_pass(c, B, (uint32_t)c->plan.size(), &local);
         if (!rc) rc = queue_totals(c, B);
-        if (!rc) rc = retire_pass(c, B, s, &local);
+        if (!rc) rc = start_copy(c, B, s, &local);
+        if (!rc) rc = finish_copy(c, B, s);
         if (rc) return rc;
         local.text_bytes += piece;
         done += piece;

@@ -250,15 +250,41 @@ __device__ __forceinline__ void cmp_words(const uint4 r, uint32_t thr, uint32_t 
     }
 }
 
-// Linear CRC of every row prefix (register starts at 0, no final xor); run once per set_snps.
+// Linear CRC of every row prefix (register starts at 0, no final xor), and the set of byte values that occur in
+// the prefixes (the code tables must hold a literal for each); run once per set_snps.
+// state: [0..7] presence bits, [8] blocks finished (zeroed by the host); the last block stores the set to
+// host_present (mapped page-locked memory), so that no DMA read-back is needed.
 __global__ void __launch_bounds__(256) k_prefix_crc(const uint8_t* __restrict__ prefix, const uint64_t* __restrict__ pre_off,
                                                    uint64_t n_rows, const uint32_t* __restrict__ crctab,
-                                                   uint32_t* __restrict__ out) {
+                                                   uint32_t* __restrict__ out, uint32_t* __restrict__ state,
+                                                   volatile uint32_t* __restrict__ host_present) {
     const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n_rows) return;
-    uint32_t c = 0;
-    for (uint64_t i = pre_off[r]; i < pre_off[r + 1]; ++i) c = __ldg(&crctab[(c ^ prefix[i]) & 0xFFu]) ^ (c >> 8);
-    out[r] = c;
+    uint32_t seen[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (r < n_rows) {
+        uint32_t c = 0;
+        for (uint64_t i = pre_off[r]; i < pre_off[r + 1]; ++i) {
+            const uint32_t v = prefix[i];
+            c = __ldg(&crctab[(c ^ v) & 0xFFu]) ^ (c >> 8);
+#pragma unroll
+            for (int w = 0; w < 8; ++w)
+                if ((v >> 5) == (uint32_t)w) seen[w] |= 1u << (v & 31u);
+        }
+        out[r] = c;
+    }
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        const uint32_t m = __reduce_or_sync(0xFFFFFFFFu, seen[w]);
+        if ((threadIdx.x & 31u) == 0 && m) atomicOr(&state[w], m);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&state[8], 1u) + 1u == gridDim.x) {
+            __threadfence();
+            for (int w = 0; w < 8; ++w) host_present[w] = *reinterpret_cast<volatile uint32_t*>(&state[w]);
+            __threadfence_system();
+        }
+    }
 }
 
 __device__ __forceinline__ uint32_t mul_tab(const uint32_t* __restrict__ t, uint32_t v) {   // t: [4][256]

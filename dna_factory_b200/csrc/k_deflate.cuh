@@ -416,12 +416,7 @@ __global__ void __launch_bounds__(1024) k_scan_sizes(const uint32_t* __restrict_
 }
 
 // Gathers slot b into the contiguous stream at offsets[b].
-__global__ void __launch_bounds__(256) k_compact(const uint8_t* __restrict__ slots, uint32_t slot_stride,
-                                                const uint32_t* __restrict__ sizes, const uint64_t* __restrict__ offsets,
-                                                uint8_t* __restrict__ out) {
-    const uint8_t* src = slots + (uint64_t)blockIdx.x * slot_stride + kSlotLead;
-    uint8_t* dst = out + offsets[blockIdx.x];
-    const uint32_t n = sizes[blockIdx.x];
+__device__ __forceinline__ void copy_block(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint32_t n) {
     // 16-byte stores to the destination; the source (slot + kSlotLead) is read as 16-bit units
     const uint32_t head = min(n, (uint32_t)((16u - (reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u));
     for (uint32_t i = threadIdx.x; i < head; i += blockDim.x) dst[i] = src[i];
@@ -446,6 +441,94 @@ __global__ void __launch_bounds__(256) k_compact(const uint8_t* __restrict__ slo
         d16[i] = make_uint4(w[0], w[1], w[2], w[3]);
     }
     for (uint32_t i = head + body * 16u + threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
+
+__global__ void __launch_bounds__(256) k_compact(const uint8_t* __restrict__ slots, uint32_t slot_stride,
+                                                const uint32_t* __restrict__ sizes, const uint64_t* __restrict__ offsets,
+                                                uint8_t* __restrict__ out) {
+    copy_block(slots + (uint64_t)blockIdx.x * slot_stride + kSlotLead, out + offsets[blockIdx.x], sizes[blockIdx.x]);
+}
+
+// Scan + gather in one launch: a CTA takes the next tile of kTile slots (ticket order), publishes the tile's
+// byte count, finds the bytes before it by decoupled look-back over the tiles in front, and copies its slots.
+// state: [0] total bytes, [1] xor of the block CRC32s, [2] ticket counter, [3] tiles finished, [4 + t] tile t:
+// status << 62 | bytes (status 1: the tile's own bytes, 2: all bytes up to and including the tile).  The host zeroes
+// it per pass.  The last tile to finish stores the two totals to `host_totals` (mapped page-locked memory): a
+// DMA read-back would queue behind the previous pass's data copy on the device-to-host copy engine.
+constexpr uint32_t kTile = 8;
+__global__ void __launch_bounds__(256) k_scan_compact(const uint8_t* __restrict__ slots, uint32_t slot_stride,
+                                                     const uint32_t* __restrict__ sizes, const uint32_t* __restrict__ crcs,
+                                                     uint32_t nb, unsigned long long* __restrict__ state,
+                                                     volatile unsigned long long* __restrict__ host_totals,
+                                                     uint8_t* __restrict__ out) {
+    __shared__ uint32_t s_tile;
+    __shared__ uint64_t s_off[kTile];
+    __shared__ uint32_t s_size[kTile];
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0) s_tile = (uint32_t)atomicAdd(&state[2], 1ull);
+    __syncthreads();
+    const uint32_t tile = s_tile, ntiles = (nb + kTile - 1u) / kTile;
+    volatile unsigned long long* agg = state + 4;
+    if (tid < 32) {
+        const uint32_t b = tile * kTile + tid;
+        const uint32_t sz = (tid < kTile && b < nb) ? sizes[b] : 0u;
+        uint32_t x = (tid < kTile && b < nb) ? crcs[b] : 0u;
+        uint32_t v = sz;
+#pragma unroll
+        for (int o = 1; o < (int)kTile; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, v, o);
+            if (tid >= (uint32_t)o) v += u;
+        }
+        x = warp_xor(x);
+        const uint64_t mine = __shfl_sync(0xFFFFFFFFu, v, kTile - 1);   // bytes of this tile
+        if (tid == 0) {
+            agg[tile] = ((tile == 0 ? 2ull : 1ull) << 62) | mine;
+            __threadfence();
+            if (x) atomicXor(&state[1], (unsigned long long)x);
+        }
+        // look back: lane l inspects tile (look - l); stop at the first tile that already knows its inclusive prefix
+        uint64_t before = 0;
+        int look = (int)tile - 1;
+        while (look >= 0) {
+            const int t = look - (int)tid;
+            unsigned long long a = 2ull << 62;   // lanes in front of tile 0 count as "inclusive, zero bytes"
+            if (t >= 0) {
+                do { a = agg[t]; } while ((a >> 62) == 0ull);
+            }
+            const uint32_t incl = __ballot_sync(0xFFFFFFFFu, (a >> 62) == 2ull);
+            const uint32_t first = incl ? (uint32_t)__ffs((int)incl) - 1u : 32u;   // lanes 0..first count
+            uint64_t part = tid <= first ? (a & ((1ull << 62) - 1ull)) : 0ull;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
+            before += part;
+            if (incl) break;
+            look -= 32;
+        }
+        if (tid == 0 && tile != 0) {
+            agg[tile] = (2ull << 62) | (before + mine);
+            __threadfence();
+        }
+        if (tid == 0 && tile + 1u == ntiles) state[0] = before + mine;
+        if (tid < kTile) {
+            s_off[tid] = before + v - sz;
+            s_size[tid] = sz;
+        }
+    }
+    __syncthreads();
+    for (uint32_t k = 0; k < kTile; ++k) {
+        const uint32_t b = tile * kTile + k;
+        if (b >= nb) break;
+        copy_block(slots + (uint64_t)b * slot_stride + kSlotLead, out + s_off[k], s_size[k]);
+    }
+    if (tid == 0) {   // totals are final once every tile has added its share
+        __threadfence();
+        if (atomicAdd(&state[3], 1ull) + 1ull == (unsigned long long)ntiles) {
+            __threadfence();
+            host_totals[0] = *reinterpret_cast<volatile unsigned long long*>(&state[0]);
+            host_totals[1] = *reinterpret_cast<volatile unsigned long long*>(&state[1]);
+            __threadfence_system();
+        }
+    }
 }
 
 }  // namespace dnaf

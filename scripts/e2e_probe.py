@@ -10,7 +10,7 @@ sex, ctl, table, orow, osamp = bench.synth_population(6 * R, 0, window=R)
 arrays = table.device_arrays()
 eng = _native.Engine(0)
 eng.set_samples(sex, ctl)
-out = torch.empty(200 << 20, dtype=torch.uint8, pin_memory=True).numpy()
+out = torch.empty(400 << 20, dtype=torch.uint8, pin_memory=True).numpy()
 
 def batch(k):
     lo, hi = k * R, (k + 1) * R
