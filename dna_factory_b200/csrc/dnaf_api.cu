@@ -961,7 +961,8 @@ int generate_impl(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t se
         const int cur = npass % 3;
         rc = finish_copy(c, c->ob[cur], sink);
         if (rc) return rc;
-        const uint64_t r1 = next_chunk_end(c, r0, row_end, c->chunk_bytes);
+        // the first passes of a call are short (1/8, 1/4, 1/2 of a chunk): the GPU starts while the host still plans
+        const uint64_t r1 = next_chunk_end(c, r0, row_end, std::max<uint64_t>(c->chunk_bytes >> std::max(0, 3 - npass), 4096));
         dnaf_ctx::OutBuf& B = c->ob[cur];
         const auto t_plan0 = std::chrono::steady_clock::now();
         plan_pass(c, r0, r1, c->h_k.data());

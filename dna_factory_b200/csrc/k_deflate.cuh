@@ -417,28 +417,28 @@ __global__ void __launch_bounds__(1024) k_scan_sizes(const uint32_t* __restrict_
 
 // Gathers slot b into the contiguous stream at offsets[b].
 __device__ __forceinline__ void copy_block(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint32_t n) {
-    // 16-byte stores to the destination; the source (slot + kSlotLead) is read as 16-bit units
+    // 16-byte stores to the destination; the source is read as ALIGNED 16-byte words too and shifted into place
+    // (reads may run up to 31 bytes past the block's last byte: still inside its 64 KiB slot)
     const uint32_t head = min(n, (uint32_t)((16u - (reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u));
     for (uint32_t i = threadIdx.x; i < head; i += blockDim.x) dst[i] = src[i];
     const uint32_t body = (n - head) / 16u;
     uint4* d16 = reinterpret_cast<uint4*>(dst + head);
+    const uintptr_t sa = reinterpret_cast<uintptr_t>(src + head);
+    const uint4* s16 = reinterpret_cast<const uint4*>(sa & ~uintptr_t(15));
+    const uint32_t mis = (uint32_t)(sa & 15u), wsh = mis >> 2, bsh = (mis & 3u) * 8u;   // uniform over the block
     for (uint32_t i = threadIdx.x; i < body; i += blockDim.x) {
-        const uint8_t* p = src + head + 16u * i;
-        uint32_t w[4];
-        if ((reinterpret_cast<uintptr_t>(p) & 3u) == 0) {
-            const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
+        const uint4 A = s16[i];
+        uint4 B = A;
+        if (mis) B = s16[i + 1];
+        const uint32_t w[9] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w, 0u};
+        uint32_t o[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) w[k] = q[k];
-        } else if ((reinterpret_cast<uintptr_t>(p) & 1u) == 0) {
-            const uint16_t* q = reinterpret_cast<const uint16_t*>(p);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) w[k] = q[2 * k] | ((uint32_t)q[2 * k + 1] << 16);
-        } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                w[k] = p[4 * k] | (p[4 * k + 1] << 8) | (p[4 * k + 2] << 16) | ((uint32_t)p[4 * k + 3] << 24);
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t lo = wsh == 0 ? w[k] : (wsh == 1 ? w[k + 1] : (wsh == 2 ? w[k + 2] : w[k + 3]));
+            const uint32_t hi = wsh == 0 ? w[k + 1] : (wsh == 1 ? w[k + 2] : (wsh == 2 ? w[k + 3] : w[k + 4]));
+            o[k] = __funnelshift_r(lo, hi, bsh);
         }
-        d16[i] = make_uint4(w[0], w[1], w[2], w[3]);
+        d16[i] = make_uint4(o[0], o[1], o[2], o[3]);
     }
     for (uint32_t i = head + body * 16u + threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
 }
