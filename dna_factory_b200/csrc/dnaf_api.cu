@@ -763,7 +763,7 @@ int reserve_outputs(dnaf_ctx* c, dnaf_ctx::OutBuf& B, uint32_t nb_exact) {
     CU(c, c->d_slots.reserve((size_t)nb * kSlot));
     CU(c, c->d_sizes.reserve(nb * sizeof(uint32_t)));
     CU(c, c->d_crcs.reserve(nb * sizeof(uint32_t)));
-    CU(c, B.d_totals.reserve((4 + (size_t)(nb + kTile - 1u) / kTile) * sizeof(uint64_t)));   // scan state of k_scan_compact
+    CU(c, B.d_totals.reserve((2 + 2 * (size_t)((nb + kGroup - 1u) / kGroup)) * sizeof(uint64_t)));   // state of k_size_partials / k_gather
     CU(c, B.d_out.reserve((size_t)nb * kSlot));
     CU(c, B.h_totals.reserve(2 * sizeof(uint64_t)));
     if (!c->attr_done) {
@@ -793,12 +793,13 @@ int launch_generic(dnaf_ctx* c, dnaf_stats* st) {
 int close_pass(dnaf_ctx* c, dnaf_ctx::OutBuf& B, uint32_t nb, dnaf_stats* st) {
     B.nb = nb;
     if (nb) {
-        const uint32_t ntiles = (nb + kTile - 1u) / kTile;
-        CU(c, cudaMemsetAsync(B.d_totals.p, 0, (4 + (size_t)ntiles) * sizeof(uint64_t), c->stream));
-        k_scan_compact<<<ntiles, 256, 0, c->stream>>>(c->d_slots.as<uint8_t>(), kSlot, c->d_sizes.as<uint32_t>(),
-                                                      c->d_crcs.as<uint32_t>(), nb,
-                                                      reinterpret_cast<unsigned long long*>(B.d_totals.p),
-                                                      reinterpret_cast<unsigned long long*>(B.h_totals.p), B.d_out.as<uint8_t>());
+        const uint32_t ntiles = (nb + kTile - 1u) / kTile, ngroups = (nb + kGroup - 1u) / kGroup;
+        k_size_partials<<<ngroups, kGroup, 0, c->stream>>>(c->d_sizes.as<uint32_t>(), c->d_crcs.as<uint32_t>(), nb,
+                                                           reinterpret_cast<unsigned long long*>(B.d_totals.p));
+        k_gather<<<ntiles, 256, 0, c->stream>>>(c->d_slots.as<uint8_t>(), kSlot, c->d_sizes.as<uint32_t>(), nb,
+                                                reinterpret_cast<unsigned long long*>(B.d_totals.p),
+                                                reinterpret_cast<unsigned long long*>(B.h_totals.p), B.d_out.as<uint8_t>());
+        if (st) st->kernel_launches += 2;
         if (st) st->kernel_launches += 1;
     }
     CU(c, cudaEventRecord(B.ev[5], c->stream));

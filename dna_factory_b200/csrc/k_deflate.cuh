@@ -416,17 +416,19 @@ __global__ void __launch_bounds__(1024) k_scan_sizes(const uint32_t* __restrict_
 }
 
 // Gathers slot b into the contiguous stream at offsets[b].
-__device__ __forceinline__ void copy_block(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint32_t n) {
+__device__ __forceinline__ void copy_block(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint32_t n,
+                                           uint32_t tid, uint32_t nthr) {
     // 16-byte stores to the destination; the source is read as ALIGNED 16-byte words too and shifted into place
     // (reads may run up to 31 bytes past the block's last byte: still inside its 64 KiB slot)
     const uint32_t head = min(n, (uint32_t)((16u - (reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u));
-    for (uint32_t i = threadIdx.x; i < head; i += blockDim.x) dst[i] = src[i];
+    for (uint32_t i = tid; i < head; i += nthr) dst[i] = src[i];
     const uint32_t body = (n - head) / 16u;
     uint4* d16 = reinterpret_cast<uint4*>(dst + head);
     const uintptr_t sa = reinterpret_cast<uintptr_t>(src + head);
     const uint4* s16 = reinterpret_cast<const uint4*>(sa & ~uintptr_t(15));
     const uint32_t mis = (uint32_t)(sa & 15u), wsh = mis >> 2, bsh = (mis & 3u) * 8u;   // uniform over the block
-    for (uint32_t i = threadIdx.x; i < body; i += blockDim.x) {
+#pragma unroll 4
+    for (uint32_t i = tid; i < body; i += nthr) {
         const uint4 A = s16[i];
         uint4 B = A;
         if (mis) B = s16[i + 1];
@@ -440,94 +442,100 @@ __device__ __forceinline__ void copy_block(const uint8_t* __restrict__ src, uint
         }
         d16[i] = make_uint4(o[0], o[1], o[2], o[3]);
     }
-    for (uint32_t i = head + body * 16u + threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+    for (uint32_t i = head + body * 16u + tid; i < n; i += nthr) dst[i] = src[i];
 }
 
 __global__ void __launch_bounds__(256) k_compact(const uint8_t* __restrict__ slots, uint32_t slot_stride,
                                                 const uint32_t* __restrict__ sizes, const uint64_t* __restrict__ offsets,
                                                 uint8_t* __restrict__ out) {
-    copy_block(slots + (uint64_t)blockIdx.x * slot_stride + kSlotLead, out + offsets[blockIdx.x], sizes[blockIdx.x]);
+    copy_block(slots + (uint64_t)blockIdx.x * slot_stride + kSlotLead, out + offsets[blockIdx.x], sizes[blockIdx.x], threadIdx.x, blockDim.x);
 }
 
-// Scan + gather in one launch: a CTA takes the next tile of kTile slots (ticket order), publishes the tile's
-// byte count, finds the bytes before it by decoupled look-back over the tiles in front, and copies its slots.
-// state: [0] total bytes, [1] xor of the block CRC32s, [2] ticket counter, [3] tiles finished, [4 + t] tile t:
-// status << 62 | bytes (status 1: the tile's own bytes, 2: all bytes up to and including the tile).  The host zeroes
-// it per pass.  The last tile to finish stores the two totals to `host_totals` (mapped page-locked memory): a
-// DMA read-back would queue behind the previous pass's data copy on the device-to-host copy engine.
+// Scan + gather without any inter-CTA dependency:
+//   k_size_partials: one CTA per 256 slots sums their byte counts and xors their CRC32s
+//   k_gather:        a CTA takes kTile slots; the bytes in front of them are the partial sums in front of their
+//                    256-slot group plus the sizes inside the group in front of the tile -- at most 105 + 255
+//                    values, read in parallel -- then one warp per slot copies.  The CTA of the last tile stores
+//                    the two totals to `host_totals` (mapped page-locked memory): a DMA read-back would queue
+//                    behind the previous pass's data copy on the device-to-host copy engine.
+// state: [g] bytes of slot group g, [ngroups + g] xor of its CRC32s (every word is written before it is read).
 constexpr uint32_t kTile = 8;
-__global__ void __launch_bounds__(256) k_scan_compact(const uint8_t* __restrict__ slots, uint32_t slot_stride,
-                                                     const uint32_t* __restrict__ sizes, const uint32_t* __restrict__ crcs,
-                                                     uint32_t nb, unsigned long long* __restrict__ state,
-                                                     volatile unsigned long long* __restrict__ host_totals,
-                                                     uint8_t* __restrict__ out) {
-    __shared__ uint32_t s_tile;
+constexpr uint32_t kGroup = 256;
+__global__ void __launch_bounds__(kGroup) k_size_partials(const uint32_t* __restrict__ sizes, const uint32_t* __restrict__ crcs,
+                                                         uint32_t nb, unsigned long long* __restrict__ state) {
+    __shared__ uint32_t s_sum[8], s_xor[8];
+    const uint32_t b = blockIdx.x * kGroup + threadIdx.x;
+    uint32_t v = b < nb ? sizes[b] : 0u, x = b < nb ? crcs[b] : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    x = warp_xor(x);
+    if ((threadIdx.x & 31u) == 0) { s_sum[threadIdx.x >> 5] = v; s_xor[threadIdx.x >> 5] = x; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t t = 0;
+        uint32_t xx = 0;
+        for (int w = 0; w < 8; ++w) { t += s_sum[w]; xx ^= s_xor[w]; }
+        state[blockIdx.x] = t;
+        state[gridDim.x + blockIdx.x] = xx;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_gather(const uint8_t* __restrict__ slots, uint32_t slot_stride,
+                                               const uint32_t* __restrict__ sizes, uint32_t nb,
+                                               const unsigned long long* __restrict__ state,
+                                               volatile unsigned long long* __restrict__ host_totals,
+                                               uint8_t* __restrict__ out) {
+    __shared__ uint64_t s_part[8];
+    __shared__ uint32_t s_xor[8];
     __shared__ uint64_t s_off[kTile];
     __shared__ uint32_t s_size[kTile];
-    const uint32_t tid = threadIdx.x;
-    if (tid == 0) s_tile = (uint32_t)atomicAdd(&state[2], 1ull);
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    const uint32_t tile = blockIdx.x, first = tile * kTile, group = first / kGroup, g0 = group * kGroup;
+    // bytes of the slot groups in front (strided over the CTA), plus the slots of this group in front of the tile
+    uint64_t acc = 0;
+    for (uint32_t g = tid; g < group; g += 256u) acc += state[g];
+    const uint32_t b = g0 + tid;
+    if (b < first) acc += sizes[b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+    if (lane == 0) s_part[wid] = acc;
+    const uint32_t sz = (tid < kTile && first + tid < nb) ? sizes[first + tid] : 0u;
+    const bool last_tile = first + kTile >= nb;
+    const uint32_t ngroups = (nb + kGroup - 1u) / kGroup;
+    uint32_t xx = 0;
+    if (last_tile) {   // checksum of checksums
+        for (uint32_t g = tid; g < ngroups; g += 256u) xx ^= (uint32_t)state[ngroups + g];
+        xx = warp_xor(xx);
+        if (lane == 0) s_xor[wid] = xx;
+    }
     __syncthreads();
-    const uint32_t tile = s_tile, ntiles = (nb + kTile - 1u) / kTile;
-    volatile unsigned long long* agg = state + 4;
     if (tid < 32) {
-        const uint32_t b = tile * kTile + tid;
-        const uint32_t sz = (tid < kTile && b < nb) ? sizes[b] : 0u;
-        uint32_t x = (tid < kTile && b < nb) ? crcs[b] : 0u;
+        uint64_t before = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) before += s_part[w];
         uint32_t v = sz;
 #pragma unroll
         for (int o = 1; o < (int)kTile; o <<= 1) {
             const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, v, o);
             if (tid >= (uint32_t)o) v += u;
         }
-        x = warp_xor(x);
-        const uint64_t mine = __shfl_sync(0xFFFFFFFFu, v, kTile - 1);   // bytes of this tile
-        if (tid == 0) {
-            agg[tile] = ((tile == 0 ? 2ull : 1ull) << 62) | mine;
-            __threadfence();
-            if (x) atomicXor(&state[1], (unsigned long long)x);
-        }
-        // look back: lane l inspects tile (look - l); stop at the first tile that already knows its inclusive prefix
-        uint64_t before = 0;
-        int look = (int)tile - 1;
-        while (look >= 0) {
-            const int t = look - (int)tid;
-            unsigned long long a = 2ull << 62;   // lanes in front of tile 0 count as "inclusive, zero bytes"
-            if (t >= 0) {
-                do { a = agg[t]; } while ((a >> 62) == 0ull);
-            }
-            const uint32_t incl = __ballot_sync(0xFFFFFFFFu, (a >> 62) == 2ull);
-            const uint32_t first = incl ? (uint32_t)__ffs((int)incl) - 1u : 32u;   // lanes 0..first count
-            uint64_t part = tid <= first ? (a & ((1ull << 62) - 1ull)) : 0ull;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
-            before += part;
-            if (incl) break;
-            look -= 32;
-        }
-        if (tid == 0 && tile != 0) {
-            agg[tile] = (2ull << 62) | (before + mine);
-            __threadfence();
-        }
-        if (tid == 0 && tile + 1u == ntiles) state[0] = before + mine;
         if (tid < kTile) {
             s_off[tid] = before + v - sz;
             s_size[tid] = sz;
         }
-    }
-    __syncthreads();
-    for (uint32_t k = 0; k < kTile; ++k) {
-        const uint32_t b = tile * kTile + k;
-        if (b >= nb) break;
-        copy_block(slots + (uint64_t)b * slot_stride + kSlotLead, out + s_off[k], s_size[k]);
-    }
-    if (tid == 0) {   // totals are final once every tile has added its share
-        __threadfence();
-        if (atomicAdd(&state[3], 1ull) + 1ull == (unsigned long long)ntiles) {
-            __threadfence();
-            host_totals[0] = *reinterpret_cast<volatile unsigned long long*>(&state[0]);
-            host_totals[1] = *reinterpret_cast<volatile unsigned long long*>(&state[1]);
+        if (tid == kTile - 1u && last_tile) {   // totals
+            uint32_t x = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) x ^= s_xor[w];
+            host_totals[0] = before + v;
+            host_totals[1] = x;
             __threadfence_system();
         }
+    }
+    __syncthreads();
+    {   // one warp per slot of the tile: eight independent copies in flight per CTA
+        const uint32_t k = wid, bb = first + k;
+        if (bb < nb) copy_block(slots + (uint64_t)bb * slot_stride + kSlotLead, out + s_off[k], s_size[k], lane, 32u);
     }
 }
 
