@@ -37,7 +37,7 @@ class DnafError(RuntimeError):
 EXPORTS = ["dnaf_abi_version", "dnaf_last_error", "dnaf_create", "dnaf_destroy", "dnaf_set_stream",
            "dnaf_set_chunk_bytes", "dnaf_set_row_base", "dnaf_set_fused", "dnaf_set_samples", "dnaf_set_snps", "dnaf_set_overrides",
            "dnaf_plan", "dnaf_generate", "dnaf_generate_stream", "dnaf_generate_device", "dnaf_genotypes",
-           "dnaf_text", "dnaf_bgzf_compress", "dnaf_bgzf_bound", "dnaf_bgzf_eof"]
+           "dnaf_text", "dnaf_bgzf_compress", "dnaf_bgzf_bound", "dnaf_bgzf_eof", "dnaf_select_snps"]
 
 _lib = None
 
@@ -54,6 +54,7 @@ def load():
     vp, u8p, u32p, u64p = ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint8), ctypes.POINTER(ctypes.c_uint32), \
         ctypes.POINTER(ctypes.c_uint64)
     u64, i32 = ctypes.c_uint64, ctypes.c_int
+    f64p = ctypes.POINTER(ctypes.c_double)
     sp = ctypes.POINTER(Stats)
     sig = {
         "dnaf_abi_version": (i32, []),
@@ -76,6 +77,8 @@ def load():
         "dnaf_bgzf_compress": (i32, [vp, u8p, u64, i32, u8p, u64, sp]),
         "dnaf_bgzf_bound": (u64, [u64]),
         "dnaf_bgzf_eof": (i32, [u8p]),
+        "dnaf_select_snps": (i32, [vp, u64, u64, ctypes.c_uint32, f64p, f64p, u8p, ctypes.c_uint32, f64p, i32, u32p, u8p, u8p,
+                                   u32p, u8p, u8p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -162,6 +165,24 @@ class Engine:
             raise ValueError("rows and samples differ in length")
         self._check(self._lib.dnaf_set_overrides(self._h, len(rows), rows.ctypes.data_as(
             ctypes.POINTER(ctypes.c_uint64)), samples.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32))))
+
+    # -- SNP selection (SnpFactory.random_snp_tuples + the sort of pop_factory.py:245, on the GPU)
+    def select_snps(self, n, seed, chrom_cdf, chrom_max_pos, chrom_rank, maf_cdf, sort=True):
+        """-> dict of columns in final order: order (draw index), chrom_idx, maf_bin, position, ref, alt."""
+        ccdf = np.ascontiguousarray(chrom_cdf, dtype=np.float64)
+        cmax = np.ascontiguousarray(chrom_max_pos, dtype=np.float64)
+        rank = np.ascontiguousarray(chrom_rank, dtype=np.uint8)
+        mcdf = np.ascontiguousarray(maf_cdf, dtype=np.float64)
+        if not (len(ccdf) == len(cmax) == len(rank)):
+            raise ValueError("chromosome arrays differ in length")
+        out = dict(order=np.empty(n, np.uint32), chrom_idx=np.empty(n, np.uint8), maf_bin=np.empty(n, np.uint8),
+                   position=np.empty(n, np.uint32), ref=np.empty(n, np.uint8), alt=np.empty(n, np.uint8))
+        f64p, u32p = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint32)
+        self._check(self._lib.dnaf_select_snps(
+            self._h, n, seed, len(ccdf), ccdf.ctypes.data_as(f64p), cmax.ctypes.data_as(f64p), _u8(rank), len(mcdf),
+            mcdf.ctypes.data_as(f64p), 1 if sort else 0, out["order"].ctypes.data_as(u32p), _u8(out["chrom_idx"]),
+            _u8(out["maf_bin"]), out["position"].ctypes.data_as(u32p), _u8(out["ref"]), _u8(out["alt"])))
+        return out
 
     # -- sizes
     def plan(self, row_begin, row_end):

@@ -23,6 +23,7 @@
 #include "k_fused_text.cuh"
 #include "k_fused_x.cuh"
 #include "k_sample_format.cuh"
+#include "k_select.cuh"
 #include <map>
 #include <unordered_map>
 
@@ -1350,6 +1351,88 @@ int dnaf_set_overrides(dnaf_ctx* c, uint64_t P, const uint64_t* rows, const uint
     if (!rc) rc = upload(c, c->d_osamp, samples, P);
     if (rc) return rc;
     c->P = P;
+    return DNAF_OK;
+}
+
+int dnaf_select_snps(dnaf_ctx* c, uint64_t n, uint64_t seed, uint32_t n_chrom, const double* chrom_cdf,
+                     const double* chrom_max_pos, const uint8_t* chrom_rank, uint32_t n_maf, const double* maf_cdf,
+                     int sorted, uint32_t* order, uint8_t* chrom_idx, uint8_t* maf_bin, uint32_t* position, uint8_t* ref,
+                     uint8_t* alt) {
+    if (!c) return DNAF_E_ARG;
+    if (n == 0) return DNAF_OK;
+    if (n > 0xFFFFFFFFull) return fail(c, DNAF_E_ARG, "at most 2^32-1 SNPs per call");
+    if (!chrom_cdf || !chrom_max_pos || !chrom_rank || !maf_cdf || !order || !chrom_idx || !maf_bin || !position || !ref || !alt)
+        return fail(c, DNAF_E_ARG, "NULL array");
+    if (n_chrom < 1 || n_chrom > (uint32_t)kSelMaxChrom || n_maf < 1 || n_maf > (uint32_t)kSelMaxMaf)
+        return fail(c, DNAF_E_ARG, "1..%d chromosomes and 1..%d MAF bins", kSelMaxChrom, kSelMaxMaf);
+    for (uint32_t i = 0; i < n_chrom; ++i)
+        if (!(chrom_max_pos[i] >= 0.0) || chrom_max_pos[i] >= 4294967296.0) return fail(c, DNAF_E_ARG, "chromosome length out of range");
+    CU(c, cudaSetDevice(c->dev));
+    DevBuf d_par, d_key, d_key2, d_idx, d_idx2, d_col, d_col2, d_tmp;
+    const size_t par_bytes = (2 * (size_t)n_chrom + n_maf) * sizeof(double) + n_chrom;
+    std::vector<uint8_t> par(par_bytes);
+    memcpy(par.data(), chrom_cdf, n_chrom * sizeof(double));
+    memcpy(par.data() + n_chrom * sizeof(double), chrom_max_pos, n_chrom * sizeof(double));
+    memcpy(par.data() + 2 * n_chrom * sizeof(double), maf_cdf, n_maf * sizeof(double));
+    memcpy(par.data() + (2 * (size_t)n_chrom + n_maf) * sizeof(double), chrom_rank, n_chrom);
+    int rc = upload(c, d_par, par.data(), par.size(), false);
+    if (rc) return rc;
+    const size_t col_bytes = n * 8 + 64;   // chrom, maf, ref, alt (1 byte each) + pos (4 bytes), 16-byte aligned pieces
+    auto col_at = [&](DevBuf& b, int which) {   // 0 pos, 1 chrom, 2 maf, 3 ref, 4 alt
+        uint8_t* p = b.as<uint8_t>();
+        const size_t n4 = (n * 4 + 15) & ~size_t(15), n1 = (n + 15) & ~size_t(15);
+        return which == 0 ? p : p + n4 + (size_t)(which - 1) * n1;
+    };
+    CU(c, d_key.reserve(n * 8));
+    CU(c, d_key2.reserve(n * 8));
+    CU(c, d_idx.reserve(n * 4));
+    CU(c, d_idx2.reserve(n * 4));
+    CU(c, d_col.reserve(col_bytes + 64));
+    CU(c, d_col2.reserve(col_bytes + 64));
+    SelectArgs a;
+    a.n = n;
+    a.k0 = (uint32_t)seed;
+    a.k1 = (uint32_t)(seed >> 32);
+    a.n_chrom = n_chrom;
+    a.n_maf = n_maf;
+    a.chrom_cdf = d_par.as<double>();
+    a.chrom_max_pos = d_par.as<double>() + n_chrom;
+    a.maf_cdf = d_par.as<double>() + 2 * n_chrom;
+    a.chrom_rank = d_par.as<uint8_t>() + (2 * (size_t)n_chrom + n_maf) * sizeof(double);
+    a.key = d_key.as<uint64_t>();
+    a.idx = d_idx.as<uint32_t>();
+    a.pos = reinterpret_cast<uint32_t*>(col_at(d_col, 0));
+    a.chrom = col_at(d_col, 1);
+    a.maf = col_at(d_col, 2);
+    a.ref = col_at(d_col, 3);
+    a.alt = col_at(d_col, 4);
+    k_select_snps<<<(uint32_t)((n + 255) / 256), 256, 0, c->stream>>>(a);
+    CU(c, cudaGetLastError());
+    const DevBuf* res = &d_col;
+    const uint32_t* d_order = d_idx.as<uint32_t>();
+    if (sorted) {
+        // stable LSD radix sort on (string rank of the chromosome, position): ties keep draw order, like list.sort
+        size_t tmp = 0;
+        CU(c, cub::DeviceRadixSort::SortPairs(nullptr, tmp, d_key.as<uint64_t>(), d_key2.as<uint64_t>(), d_idx.as<uint32_t>(),
+                                              d_idx2.as<uint32_t>(), (int)n, 0, 40, c->stream));
+        CU(c, d_tmp.reserve(tmp + 16));
+        CU(c, cub::DeviceRadixSort::SortPairs(d_tmp.p, tmp, d_key.as<uint64_t>(), d_key2.as<uint64_t>(), d_idx.as<uint32_t>(),
+                                              d_idx2.as<uint32_t>(), (int)n, 0, 40, c->stream));
+        k_select_gather<<<(uint32_t)((n + 255) / 256), 256, 0, c->stream>>>(
+            n, d_idx2.as<uint32_t>(), a.chrom, a.maf, a.pos, a.ref, a.alt, col_at(d_col2, 1), col_at(d_col2, 2),
+            reinterpret_cast<uint32_t*>(col_at(d_col2, 0)), col_at(d_col2, 3), col_at(d_col2, 4));
+        CU(c, cudaGetLastError());
+        res = &d_col2;
+        d_order = d_idx2.as<uint32_t>();
+    }
+    DevBuf& R = const_cast<DevBuf&>(*res);
+    CU(c, cudaMemcpyAsync(order, d_order, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(position, col_at(R, 0), n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(chrom_idx, col_at(R, 1), n, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(maf_bin, col_at(R, 2), n, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(ref, col_at(R, 3), n, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(alt, col_at(R, 4), n, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
     return DNAF_OK;
 }
 

@@ -172,7 +172,7 @@ class DeleteriousGroup:
 class PopulationFactory:
     def __init__(self, num_processes=1, generate_snps=False, male_odds=0.5, deleterious_config=None,
                  deleterious_list_path=None, sample_id_offset=0, snps_path=None, output_path=None, seed=None,
-                 gpus=1):
+                 gpus=1, gpu_select=False):
         self.deleterious = {}
         self.ordered_snps = []
         self.snp_table = None
@@ -190,6 +190,7 @@ class PopulationFactory:
         self.snps_path = snps_path
         self.seed = seed
         self.gpus = max(1, gpus or 1)
+        self.gpu_select = bool(gpu_select)
         self.stats = []
 
     # ------------------------------------------------------------------------------------------ orchestration
@@ -200,14 +201,22 @@ class PopulationFactory:
         if self.seed is None:
             self.seed = clock_seed
         os.makedirs(self.population_dir, exist_ok=True)
+        presorted = False
         if self.snps_path:
             self.load_snps_file()
+        elif self.generate_snps and self.gpu_select:
+            # SnpFactory.random_snp_tuples + the sort of pop_factory.py:245 on the GPU, keyed by --seed
+            with _native.Engine(0) as eng:
+                self.snp_table = SnpFactory.init_from_cdf_file().random_snp_table_device(eng, max_snps, self.seed,
+                                                                                         min_maf=min_freq)
+            presorted = True
         elif self.generate_snps:
             self.snp_table = SnpFactory.init_from_cdf_file().random_snp_table(max_snps, min_maf=min_freq)
         else:
             self.load_snps_db(min_freq, max_snps)
         if self.snp_table is not None:
-            self.snp_table = self.snp_table.sorted()
+            if not presorted:
+                self.snp_table = self.snp_table.sorted()
         else:
             self.ordered_snps.sort(key=lambda x: (x.chromosome, x.position))
         if not self.snps_path:
@@ -417,6 +426,8 @@ def parse_cmd_args(args):
     # opt-in extras of the B200 path
     ap.add_argument("--seed", type=int, default=None, help="Philox seed of the genotype draws (default: HHMMSS clock)")
     ap.add_argument("--gpus", type=int, default=1, help="GPUs to spread contiguous SNP ranges over (default 1)")
+    ap.add_argument("--gpu_select", action="store_true",
+                    help="draw and sort the simulated SNPs on the GPU from the --seed stream instead of numpy's global state")
     return ap.parse_args(args)
 
 
@@ -427,7 +438,8 @@ def main(sys_args):
     factory = PopulationFactory(num_processes=args.num_processes, generate_snps=args.generate_snps,
                                 deleterious_list_path=args.deleterious_file, sample_id_offset=args.offset,
                                 male_odds=args.male_odds, deleterious_config=args.deleterious_config,
-                                snps_path=args.snps_file, output_path=args.outdir, seed=args.seed, gpus=args.gpus)
+                                snps_path=args.snps_file, output_path=args.outdir, seed=args.seed, gpus=args.gpus,
+                                gpu_select=args.gpu_select)
     factory.generate_population(args.control_size, args.size, args.min_freq, args.max_snps, args.compression_level)
 
 

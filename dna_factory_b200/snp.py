@@ -343,3 +343,38 @@ class SnpFactory:
 
     def random_snp_tuples(self, size, min_maf=0.005):
         return self.random_snp_table(size, min_maf).to_snps()
+
+    # ---- the same selection on the GPU (counter-based stream instead of numpy's global state) ---------
+    def selection_tables(self, min_maf=0.005):
+        """What the device sampler needs: the two cumulative tables exactly as numpy.random.choice builds them
+        (cdf = p.cumsum(); cdf /= cdf[-1]), chromosome lengths and the string-order rank of every label."""
+        start = self._first_bin(min_maf)
+        p = self.pdf[start:]
+        p = p * 1 / np.sum(p)                                   # pop_factory.py:166-167
+        maf_cdf = p.cumsum()
+        maf_cdf /= maf_cdf[-1]
+        chrom_cdf = np.asarray(CHROMOSOME_PROB, dtype=np.float64).cumsum()
+        chrom_cdf /= chrom_cdf[-1]
+        labels = np.asarray(CHROMOSOME_LIST)
+        rank = np.argsort(np.argsort(labels, kind="stable"), kind="stable").astype(np.uint8)
+        max_pos = np.asarray([CHROMOSOME_MAX_POSITION[c] for c in CHROMOSOME_LIST], dtype=np.float64)
+        return dict(start=start, maf_cdf=maf_cdf, chrom_cdf=chrom_cdf, chrom_rank=rank, chrom_max_pos=max_pos)
+
+    def table_from_columns(self, cols, start, first_id=1):
+        """SnpTable from the sampler's columns (device or oracle): tuples [(ref, 1 - maf), (alt, 1.0)]."""
+        size = len(cols["order"])
+        mafs = self.sorted_maf[start:][cols["maf_bin"]]
+        nts = np.zeros((size, _native.KMAX), np.uint8)
+        nts[:, 0] = cols["ref"]
+        nts[:, 1] = cols["alt"]
+        cum = np.full((size, _native.KMAX), 2.0)
+        cum[:, 0] = 1 - mafs                                    # pop_factory.py:187
+        cum[:, 1] = 1.0
+        return SnpTable(cols["order"].astype(np.int64) + first_id, cols["chrom_idx"].astype(np.int32), CHROMOSOME_LIST,
+                        cols["position"].astype(np.int64), np.full(size, 2, np.uint8), nts, cum)
+
+    def random_snp_table_device(self, engine, size, seed, min_maf=0.005, sort=True):
+        """`size` random SNPs drawn (and, by default, sorted like pop_factory.py:245) on the GPU."""
+        t = self.selection_tables(min_maf)
+        cols = engine.select_snps(size, seed, t["chrom_cdf"], t["chrom_max_pos"], t["chrom_rank"], t["maf_cdf"], sort=sort)
+        return self.table_from_columns(cols, t["start"])

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DNAF_ABI_VERSION 1
+#define DNAF_ABI_VERSION 2
 #define DNAF_KMAX 4 /* alleles per SNP the device path handles (A,C,G,T); K=2 for SnpFactory output */
 
 /* chromosome classes -- the only thing is_haploid() (common/snp.py:102-109) looks at */
@@ -107,6 +107,22 @@ int dnaf_set_snps(dnaf_ctx* ctx, uint64_t n_snps, const uint8_t* chrom_class, co
  * The host computes them with the reference's own dict-membership semantics.
  */
 int dnaf_set_overrides(dnaf_ctx* ctx, uint64_t n_pairs, const uint64_t* snp_row, const uint32_t* sample_idx);
+
+/*
+ * SNP selection: SnpFactory.random_snp_tuples (pop_factory.py:160-193) as a GPU inverse-CDF sampler, followed
+ * (sorted != 0) by the stable sort on (chromosome label as a STRING, position) of pop_factory.py:245.
+ *   chrom_cdf[n_chrom]      cumulative CHROMOSOME_PROB as numpy.random.choice builds it (cumsum / last)
+ *   chrom_max_pos[n_chrom]  CHROMOSOME_MAX_POSITION, in CHROMOSOME_LIST order (common/snp.py:36-60)
+ *   chrom_rank[n_chrom]     rank of each label in string order ("1" < "10" < ... < "2" < ... < "X" < "Y")
+ *   maf_cdf[n_maf]          cumulative pdf[start:]/sum of the MAF grid from the -f bin on (pop_factory.py:160-167)
+ * Draw n (SNP id = n + 1) takes five uniforms from the counter-based stream; outputs are columns in
+ * final order: order[r] = draw index of row r, chrom_idx[r] (index into CHROMOSOME_LIST), maf_bin[r] (index into
+ * the grid slice), position[r], ref[r] / alt[r] (ASCII nucleotides).  Any n gives the same SNP for the same n.
+ */
+int dnaf_select_snps(dnaf_ctx* ctx, uint64_t n_snps, uint64_t seed, uint32_t n_chrom, const double* chrom_cdf,
+                     const double* chrom_max_pos, const uint8_t* chrom_rank, uint32_t n_maf, const double* maf_cdf,
+                     int sorted, uint32_t* order, uint8_t* chrom_idx, uint8_t* maf_bin, uint32_t* position,
+                     uint8_t* ref, uint8_t* alt);
 
 /* Sizes of rows [row_begin,row_end): exact text bytes and an upper bound on the BGZF bytes. */
 int dnaf_plan(dnaf_ctx* ctx, uint64_t row_begin, uint64_t row_end, uint64_t* text_bytes, uint64_t* bgzf_bound);

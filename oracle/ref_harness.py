@@ -100,3 +100,42 @@ def make_snp(snp_id, chromosome, position, tuples):
 def make_sample(index, person_id, sex, is_control, deleterious_snps, offset=0):
     ref = load()
     return ref.SampleInfo(index + 1 + offset * 2, person_id, 0, 0, sex, is_control, deleterious_snps)
+
+
+def reference_snp_selection(size, min_maf, seed):
+    """The reference's own SnpFactory.random_snp_tuples (pop_factory.py:160-193) and sort (:245), with its three
+    random sources patched to the replay stream of oracle/snp_select.py: numpy.random.choice (chromosomes, MAFs --
+    numpy's own cdf/searchsorted algorithm -- and reference nucleotides), numpy.random.random (positions) and
+    random.choice (alternate nucleotide, once per SNP in draw order).  Returns the reference's SNPTuples list."""
+    from . import snp_select
+    ref = load()
+    u = snp_select.uniforms(seed, size)
+    calls = {"choice": 0, "alt": 0}
+
+    def fake_choice(a, size=None, p=None):
+        k = calls["choice"]
+        calls["choice"] += 1
+        a = np.asarray(a)
+        if p is not None:
+            cdf = np.asarray(p, dtype=np.float64).cumsum()
+            cdf /= cdf[-1]
+            return a[cdf.searchsorted(u["chrom" if k == 0 else "maf"], side="right")]
+        return a[(u["ref"] * len(a)).astype(np.int64)]
+
+    def fake_random(n):
+        return u["pos"]
+
+    def fake_py_choice(seq):
+        i = calls["alt"]
+        calls["alt"] += 1
+        return seq[int(u["alt"][i] * len(seq))]
+
+    saved = (ref.numpy.random.choice, ref.numpy.random.random, ref.random.choice)
+    ref.numpy.random.choice, ref.numpy.random.random, ref.random.choice = fake_choice, fake_random, fake_py_choice
+    try:
+        snps = ref.SnpFactory.init_from_cdf_file().random_snp_tuples(size, min_maf=min_maf)
+    finally:
+        ref.numpy.random.choice, ref.numpy.random.random, ref.random.choice = saved
+    assert calls["choice"] == 3 and calls["alt"] == size
+    snps.sort(key=lambda x: (x.chromosome, x.position))                    # pop_factory.py:245
+    return snps

@@ -152,6 +152,20 @@ def case_single_sex():
     dump_case("all_female", 2, 7, females, snps, text)
 
 
+def case_snp_select():
+    """SnpFactory.random_snp_tuples + the sort of pop_factory.py:245, run by the reference itself with its random
+    sources patched to the selection stream (oracle/ref_harness.reference_snp_selection)."""
+    out = []
+    for size, min_maf, seed in ((3000, 0.01, 0x5EED000000000001), (1500, 0.16, 42), (1, 0.005, 3)):
+        snps = ref_harness.reference_snp_selection(size, min_maf, seed)
+        out.append({"size": size, "min_maf": min_maf, "seed": seed,
+                    "snps": [[int(s.id), str(s.chromosome), int(s.position), str(s.tuples[0][0]), float(s.tuples[0][1]),
+                              str(s.tuples[1][0]), float(s.tuples[1][1])] for s in snps]})
+    with gzip.GzipFile(os.path.join(HERE, "snp_select.json.gz"), "wb", compresslevel=9, mtime=0) as f:
+        f.write(json.dumps(out, separators=(",", ":")).encode())
+    print("snp_select     %s SNPs" % [c["size"] for c in out])
+
+
 def case_cli_small():
     """Full reference CLI run with every source of nondeterminism pinned."""
     ref = ref_harness.load()
@@ -214,6 +228,7 @@ def case_cli_small():
 
 
 if __name__ == "__main__":
+    case_snp_select()
     case_mixed64()
     case_r8_strkeys()
     case_n0()

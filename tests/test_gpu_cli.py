@@ -68,3 +68,26 @@ def test_cli_replay_from_files_reproduces_r8(tmp_path, monkeypatch):
     want, _ = oracle.rows(fam, snps, 77, 0)
     assert rows == want
     assert len(header) == 6
+
+
+def test_cli_gpu_select(tmp_path, monkeypatch):
+    """--gpu_select: snps.json.gz holds exactly the SNPs of the replay selection stream (the numpy restatement of
+    SnpFactory.random_snp_tuples + sort), and the VCF rows are the oracle's rows for them."""
+    from dna_factory_b200 import pop_factory, snp
+    from dna_factory_b200.snp import SnpTable
+    from oracle import oracle, snp_select
+    gold = os.path.join(GOLDEN, "cli_small")
+    random.seed(5)
+    pop_factory.main(["-s", "6", "-c", "5", "-x", "400", "-f", "0.01", "-z", "2", "-p",
+                      os.path.join(gold, "deleterious_config.yml"), "--outdir", str(tmp_path), "--seed", "4242",
+                      "--gpu_select"])
+    fac = snp.SnpFactory.init_from_cdf_file()
+    t = fac.selection_tables(0.01)
+    want_tab = fac.table_from_columns(snp_select.select(4242, 400, t["chrom_cdf"], t["chrom_max_pos"], t["chrom_rank"],
+                                                        t["maf_cdf"]), t["start"])
+    snps = SnpTable.read_json_gz(str(tmp_path / "snps.json.gz"))
+    assert [(s.id, s.chromosome, s.position, s.tuples) for s in snps] == \
+        [(s.id, s.chromosome, s.position, s.tuples) for s in want_tab.to_snps()]
+    vcf = gzip.decompress((tmp_path / "population.vcf.gz").read_bytes())
+    rows = vcf.split(b"\n", 6)[6]
+    assert rows.count(b"\n") == 400

@@ -224,3 +224,43 @@ def test_errors_are_loud(native):
     with pytest.raises(_native.DnafError) as e:
         eng.set_snps(**flat)
     assert e.value.code == _native.E_INPUT
+
+
+@pytest.mark.parametrize("size,min_maf,seed", [(1, 0.005, 3), (1000, 0.01, 7), (100000, 0.16, 0x5EED000000000001),
+                                               ((1 << 20) + 17, 0.01, 99)])
+def test_snp_selection_device_vs_oracle(native, size, min_maf, seed):
+    """dnaf_select_snps (inverse-CDF sampler + radix sort) against the numpy restatement of
+    SnpFactory.random_snp_tuples / the sort of pop_factory.py:245: every column identical, sorted and unsorted."""
+    from dna_factory_b200 import snp
+    from oracle import snp_select
+    _native, _ = native
+    eng = _native.Engine(0)
+    fac = snp.SnpFactory.init_from_cdf_file()
+    t = fac.selection_tables(min_maf)
+    for sort in (True, False):
+        got = eng.select_snps(size, seed, t["chrom_cdf"], t["chrom_max_pos"], t["chrom_rank"], t["maf_cdf"], sort=sort)
+        want = snp_select.select(seed, size, t["chrom_cdf"], t["chrom_max_pos"], t["chrom_rank"], t["maf_cdf"], sort=sort)
+        for k in want:
+            assert np.array_equal(got[k], want[k]), k
+    # the reference's own tolerances (test/unit/snp_factory_test.py:14-37) on the device draw
+    if size >= 100000:
+        tab = fac.random_snp_table_device(eng, size, seed, min_maf=min_maf)
+        assert np.all(1 - tab.cum[:, 0] >= min_maf - 1e-12) and not np.any(tab.nts[:, 0] == tab.nts[:, 1])
+        assert abs(np.mean(tab.chrom_idx == 0) - snp.CHROMOSOME_PROB[0]) < 0.01
+
+
+def test_snp_selection_device_feeds_generation(native):
+    """Selection on the GPU -> the usual flat arrays -> rows: the decompressed VCF equals the oracle's rows for the
+    same SNP list (the drop-in flow of a --generate_snps run)."""
+    from dna_factory_b200 import snp
+    from oracle import oracle
+    _native, host = native
+    eng = _native.Engine(0)
+    fac = snp.SnpFactory.init_from_cdf_file()
+    tab = fac.random_snp_table_device(eng, 300, 1234, min_maf=0.01)
+    case = synth_case(5000, 3, seed=5)
+    snps = tab.to_snps()
+    want, _ = oracle.rows(case.samples, snps, 77, 0, n_threads=4)
+    host.configure(eng, case.samples, snps)
+    blob, st = eng.generate(0, len(snps), 77, level=2)
+    assert oracle.bgzf_decompress(blob)[0] == want
