@@ -34,7 +34,7 @@ def build(force=False, verbose=False):
     if not force and not stale():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, os.path.join(CSRC, "dnaf_api.cu")]
+    cmd = [NVCC] + FLAGS + os.environ.get("DNAF_NVCC_EXTRA", "").split() + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, os.path.join(CSRC, "dnaf_api.cu")]
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)

@@ -21,7 +21,6 @@
 #include "k_deflate.cuh"
 #include "k_fused.cuh"
 #include "k_fused_text.cuh"
-#include "k_fused_x.cuh"
 #include "k_sample_format.cuh"
 #include "k_select.cuh"
 #include <map>
@@ -172,6 +171,9 @@ struct dnaf_ctx {
     DevBuf d_crc4, d_xspan, d_tdesc, d_xspans, d_xdesc;
     // k_auto (k_auto.cuh): code tables + byte LUTs per (bucket, starts-row), CRC move tables, per-row prefix CRCs
     DevBuf d_atables, d_etab2, d_mtab, d_mtail, d_mpre, d_xinit, d_pre_crc;
+    DevBuf d_xtables, d_mspan, d_mpre_x;   // k_x (k_x.cuh)
+    std::map<std::pair<uint64_t, uint64_t>, XTable> xtable_cache;
+    std::vector<uint32_t> h_mspan, h_mpre_x;
     std::map<std::pair<uint64_t, uint64_t>, AutoTable> atable_cache;
     std::vector<uint32_t> h_mtail, h_mpre;
     DevBuf d_pfx_state;
@@ -270,6 +272,8 @@ int ensure_layout(dnaf_ctx* c) {
     if (c->seg_tabs_dirty) {
         rc = upload(c, c->d_mtail, c->h_mtail.data(), c->h_mtail.size());
         if (!rc) rc = upload(c, c->d_mpre, c->h_mpre.data(), c->h_mpre.size());
+        if (!rc) rc = upload(c, c->d_mspan, c->h_mspan.data(), c->h_mspan.size());
+        if (!rc) rc = upload(c, c->d_mpre_x, c->h_mpre_x.data(), c->h_mpre_x.size());
         if (rc) return rc;
         c->seg_tabs_dirty = false;
     }
@@ -395,6 +399,13 @@ int ensure_tables(dnaf_ctx* c) {
         memset(tabs.data(), 0, tabs.size() * sizeof(FusedTable));
         std::vector<AutoTable> atabs((size_t)nb * 2);
         memset(atabs.data(), 0, atabs.size() * sizeof(AutoTable));
+        std::vector<XTable> xtabs;
+        bool any_x = false;
+        for (int b = 0; b < nb; ++b) any_x |= need[b * kVariants + 10] || need[b * kVariants + 11];
+        if (any_x) {
+            xtabs.resize((size_t)nb * 2);
+            memset(xtabs.data(), 0, xtabs.size() * sizeof(XTable));
+        }
         const int per_block = (int)std::max<size_t>(1, c->h_seg_cell0.size() > 1
                                                            ? (c->h_seg_cell0[1] - c->h_seg_cell0[0] + 63) / 64 : 1);
         for (int b = 0; b < nb; ++b) {
@@ -415,6 +426,18 @@ int ensure_tables(dnaf_ctx* c) {
                     atabs[(size_t)b * 2 + v] = it->second;
                     continue;
                 }
+                if (v >= 10) {   // X rows: k_x's tables
+                    auto key = std::make_pair(pbits, (with_prefix ? c->ph_hash : 0x5bd1e995ull) * 31 + (uint64_t)per_block +
+                                                         c->samples_epoch * 0x9E3779B97F4A7C15ull);
+                    auto it = c->xtable_cache.find(key);
+                    if (it == c->xtable_cache.end()) {
+                        XTable t = hosttab::make_x_table(p, c->h_xspans, per_block, with_prefix ? c->ph.data() : nullptr);
+                        if (t.hdr_bits == 0xFFFFFFFFu) return DNAF_OK;
+                        it = c->xtable_cache.emplace(key, t).first;
+                    }
+                    xtabs[(size_t)b * 2 + (v - 10)] = it->second;
+                    continue;
+                }
                 const int cls = v < 2 ? -1 : (v >= 10 ? 100 : (v - 2) / 2);   // -1: autosome cells, 100: X cells
                 const uint64_t vkey = (with_prefix ? c->ph_hash : 0x5bd1e995ull) * 31 + (uint64_t)(cls + 1) * 1000003ull +
                                       (cls >= 0 ? c->samples_epoch * 0x9E3779B97F4A7C15ull : 0);
@@ -422,9 +445,7 @@ int ensure_tables(dnaf_ctx* c) {
                 auto it = c->table_cache.find(key);
                 if (it == c->table_cache.end()) {
                     const uint64_t* hist = with_prefix ? c->ph.data() : nullptr;
-                        FusedTable t = cls < 0 ? hosttab::make_table(p, hist)
-                                   : cls == 100 ? hosttab::make_table_x(p, c->h_xspans, per_block, hist)
-                                                : hosttab::make_text_table(cls, p, c->h_sex.data(), c->n, hist);
+                        FusedTable t = hosttab::make_text_table(cls, p, c->h_sex.data(), c->n, hist);
                     if (t.hdr_bits == 0xFFFFFFFFu) return DNAF_OK;  // header too long: stay on the generic path
                     it = c->table_cache.emplace(key, t).first;
                 }
@@ -433,6 +454,7 @@ int ensure_tables(dnaf_ctx* c) {
         }
         int rc = upload(c, c->d_ftables, tabs.data(), tabs.size());
         if (!rc) rc = upload(c, c->d_atables, atabs.data(), atabs.size());
+        if (!rc && any_x) rc = upload(c, c->d_xtables, xtabs.data(), xtabs.size());
         if (rc) return rc;
         c->tables_sig = sig;
     }
@@ -546,6 +568,18 @@ void build_segments(dnaf_ctx* c) {
         const uint32_t cells0 = c->h_seg_cell0[1] - c->h_seg_cell0[0];
         hosttab::fill_mul_table(xp[4ull * cells0 - 1], c->h_mpre.data());
         hosttab::fill_mul_table(xp[4ull * cells0], c->h_mpre.data() + 1024);
+        // k_x: per span, the distance from the end of its text to the end of its segment's text; prefix -> end of segment 0
+        const size_t nsp = c->h_xspans.size();
+        c->h_mspan.assign(nsp * 1024, 0);
+        for (size_t sg = 0; sg + 1 < c->h_seg_cell0.size(); ++sg) {
+            const uint32_t seg_end = c->h_xoff[c->h_seg_cell0[sg + 1]];
+            for (size_t sp = c->h_seg_cell0[sg] / 64; sp < (c->h_seg_cell0[sg + 1] + 63u) / 64u && sp < nsp; ++sp) {
+                const uint32_t span_end = c->h_xspans[sp].byte_off + 2u * c->h_xspans[sp].L;
+                hosttab::fill_mul_table(xp[seg_end - span_end], &c->h_mspan[sp * 1024]);
+            }
+        }
+        c->h_mpre_x.assign(1024, 0);
+        hosttab::fill_mul_table(xp[c->h_xoff[c->h_seg_cell0[1]]], c->h_mpre_x.data());
         c->seg_tabs_dirty = true;
     }
     {   // X rows use the same sample segments; their template is the all-reference X body
@@ -645,7 +679,7 @@ void plan_pass(dnaf_ctx* c, uint64_t r0, uint64_t r1, const uint8_t* hk) {
                     d.body_crc = c->h_seg_crc[sgi];
                     c->fplan.push_back(d);
                 } else {
-                    d.table = (uint32_t)c->h_bucket[r] * kVariants + 10u + (sgi == 0 ? 0u : 1u);
+                    d.table = (uint32_t)c->h_bucket[r] * 2u + (sgi == 0 ? 0u : 1u);
                     d.body_crc = c->h_seg_crc_x[sgi];
                     c->xplan.push_back(d);
                 }
@@ -1029,23 +1063,25 @@ int generate_impl(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t se
         }
         if (!c->xplan.empty()) {
             XArgs xa;
-            xa.f.sv = sample_view(c);
-            xa.f.nv = snp_view(c);
-            xa.f.desc = c->d_xdesc.as<FusedDesc>();
-            xa.f.tables = c->d_ftables.as<FusedTable>();
-            xa.f.etab = c->d_etab.as<uint32_t>();
-            xa.f.crctab = c->d_crctab.as<uint32_t>();
-            xa.f.xpow8 = c->d_xpow8.as<uint32_t>();
-            xa.f.orow = c->d_orow.as<uint64_t>();
-            xa.f.osamp = c->d_osamp.as<uint32_t>();
-            xa.f.row_base = c->row_base;
-            xa.f.k0 = (uint32_t)seed;
-            xa.f.k1 = (uint32_t)(seed >> 32);
-            xa.f.slots = c->d_slots.as<uint8_t>();
-            xa.f.sizes = c->d_sizes.as<uint32_t>();
-            xa.f.crcs = c->d_crcs.as<uint32_t>();
+            xa.sv = sample_view(c);
+            xa.nv = snp_view(c);
+            xa.desc = c->d_xdesc.as<FusedDesc>();
+            xa.tables = c->d_xtables.as<XTable>();
             xa.xspans = c->d_xspans.as<XSpan>();
-            k_fused_x<<<(uint32_t)c->xplan.size(), c->fused_threads, 0, c->side>>>(xa);
+            xa.etab = c->d_etab.as<uint32_t>();
+            xa.mspan = c->d_mspan.as<uint32_t>();
+            xa.mpre = c->d_mpre_x.as<uint32_t>();
+            xa.xinit = c->d_xinit.as<uint32_t>();
+            xa.pre_crc = c->d_pre_crc.as<uint32_t>();
+            xa.orow = c->d_orow.as<uint64_t>();
+            xa.osamp = c->d_osamp.as<uint32_t>();
+            xa.row_base = c->row_base;
+            xa.k0 = (uint32_t)seed;
+            xa.k1 = (uint32_t)(seed >> 32);
+            xa.slots = c->d_slots.as<uint8_t>();
+            xa.sizes = c->d_sizes.as<uint32_t>();
+            xa.crcs = c->d_crcs.as<uint32_t>();
+            k_x<<<(uint32_t)c->xplan.size(), c->fused_threads, x_smem_bytes(c->fused_threads), c->side>>>(xa);
             local.kernel_launches += 1;
             CU(c, cudaGetLastError());
         }

@@ -15,7 +15,7 @@
 #include "k_fused.cuh"
 #include "k_auto.cuh"
 #include "k_fused_text.cuh"
-#include "k_fused_x.cuh"
+#include "k_x.cuh"
 
 namespace dnaf {
 namespace hosttab {
@@ -361,8 +361,8 @@ inline AutoTable make_auto_table(double p_minor, const uint64_t* prefix_hist, in
     return t;
 }
 
-// Static per-population description of the X-row spans (k_fused_x.cuh): compaction masks (Hacker's Delight
-// 7-4 "compress", move masks precomputed), separator kinds and separator mismatches.
+// Static per-population description of the X-row spans (k_x.cuh): compaction masks (Hacker's Delight 7-4
+// "compress", move masks precomputed), separator kinds, the per-unit separator windows and static mismatches.
 inline std::vector<XSpan> build_xspans(const uint8_t* sex, uint32_t n, const uint32_t* xoff) {
     const uint32_t nspans = (n + 63u) / 64u;
     std::vector<XSpan> out(nspans);
@@ -401,10 +401,24 @@ inline std::vector<XSpan> build_xspans(const uint8_t* sex, uint32_t n, const uin
             }
             L += xs.len[w];
         }
-        for (uint32_t k = 0; k < L; ++k) {
-            const size_t K = k0 + k;
-            if (kinds[K]) xs.sk[k >> 5] |= 1u << (k & 31u);
-            if (K < 2 || kinds[K] != kinds[K - 2]) xs.sm[k >> 5] |= 1u << (k & 31u);
+        xs.L = L;
+        // kinds of positions -2 .. 127 of the span; positions past L repeat the pair before them (no mismatch there)
+        uint8_t kk[130];
+        for (int k = -2; k < 128; ++k) {
+            uint8_t v;
+            if (k < 0) v = ((long long)k0 + k >= 0) ? kinds[(size_t)((long long)k0 + k)] : 0;
+            else if ((uint32_t)k < L) v = kinds[k0 + k];
+            else v = kk[k];                                             // = kind of position k - 2
+            kk[k + 2] = v;
+        }
+        xs.skc = (uint32_t)kk[0] | ((uint32_t)kk[1] << 1);
+        for (int k = 0; k < 128; ++k)
+            if (kk[k + 2]) xs.sk[k >> 5] |= 1u << (k & 31);
+        for (int u = 0; u < 32; ++u) {
+            uint32_t s6 = 0;
+            for (int j = 0; j < 6; ++j) s6 |= (uint32_t)kk[4 * u + j] << j;    // positions 4u-2 .. 4u+3
+            xs.sk6[u] = (uint8_t)s6;
+            if (((s6 >> 2) ^ s6) & 15u) xs.snz |= 1u << u;
         }
         xs.byte_off = xoff[i0];
         out[sp] = xs;
@@ -413,9 +427,17 @@ inline std::vector<XSpan> build_xspans(const uint8_t* sex, uint32_t n, const uin
     return out;
 }
 
-// Table for k_fused_x: token statistics of X rows with Bernoulli(p_minor) alleles over the real spans.
-inline HistSink simulate_x(double p_minor, const std::vector<XSpan>& xspans, int per_block) {
+struct XHistSink {
     HistSink h;
+    void tok(int gap) { if (gap >= 3) h.match(gap); }
+    void lit(int id) { h.lit(id); }
+    void eob() {}
+};
+
+// Table for k_x: token statistics of X rows with Bernoulli(p_minor) alleles over the population's real spans,
+// the codes, and the 4096-entry unit table.
+inline XTable make_x_table(double p_minor, const std::vector<XSpan>& xspans, int per_block, const uint64_t* prefix_hist) {
+    XHistSink hs;
     uint64_t st = 0xA24BAED4963EE407ull ^ (uint64_t)(p_minor * 1e9);
     auto next = [&]() {
         st ^= st << 13; st ^= st >> 7; st ^= st << 17;
@@ -425,27 +447,58 @@ inline HistSink simulate_x(double p_minor, const std::vector<XSpan>& xspans, int
     const size_t ns = std::min<size_t>(xspans.size(), 512);
     uint32_t carry = 0;
     for (size_t sp = 0; sp < ns; ++sp) {
+        const XSpan& xs = xspans[sp];
         uint32_t m[4], c[4];
         for (int w = 0; w < 4; ++w) {
             uint32_t v = 0;
             for (int i = 0; i < 32; ++i) v |= (uint32_t)(next() < thr) << i;
             m[w] = v;
         }
-        const uint32_t L = compact_span(m, xspans[sp], c);
+        const uint32_t L = compact_span(m, xs, c);
         if (!L) continue;
-        const bool has_prev = (sp % per_block) != 0;
-        const PairMasks pm = pair_mismatches(c, xspans[sp].sm, carry, has_prev, (int)L, false);
-        tokenize_pairs(c, xspans[sp].sk, pm, (int)L, false, h);
-        carry = L >= 2 ? ((((c[(L - 1) >> 5] >> ((L - 1) & 31)) & 1u) << 1) | ((c[(L - 2) >> 5] >> ((L - 2) & 31)) & 1u)) : 0u;
+        // pad like the kernel: positions past L repeat the pair before them
+        for (uint32_t k = L; k < 128; ++k) {
+            const uint32_t v = k >= 2 ? bit128(c, (int)k - 2) : 0u;
+            c[k >> 5] = (c[k >> 5] & ~(1u << (k & 31))) | (v << (k & 31));
+        }
+        const bool first = (sp % (size_t)std::max(1, per_block)) == 0;
+        xspan_tokens_ref(c, first ? (c[0] & 3u) : carry, xs, first, false, false, hs);
+        carry = L >= 2 ? ((bit128(c, (int)L - 1) << 1) | bit128(c, (int)L - 2)) : 0u;
     }
-    return h;
-}
-
-inline FusedTable make_table_x(double p_minor, const std::vector<XSpan>& xspans, int per_block,
-                               const uint64_t* prefix_hist) {
-    HistSink h = simulate_x(p_minor, xspans, per_block);
-    const uint64_t blocks = std::max<uint64_t>(1, std::min<size_t>(xspans.size(), 512) / (size_t)std::max(1, per_block));
-    return finish_cell_table(h, blocks, prefix_hist);
+    const uint64_t blocks = std::max<uint64_t>(1, ns / (size_t)std::max(1, per_block));
+    const FusedTable f = finish_cell_table(hs.h, blocks, prefix_hist);
+    XTable t;
+    memset(&t, 0, sizeof t);
+    t.hdr_bits = f.hdr_bits;
+    if (f.hdr_bits == 0xFFFFFFFFu) return t;
+    for (int i = 3; i < 260; ++i) t.len_tok[i] = f.len_tok[i];
+    for (int i = 0; i < 8; ++i) t.lit[i] = f.lit[i];
+    t.eob = f.eob;
+    memcpy(t.hdr, f.hdr, sizeof t.hdr);
+    memcpy(t.pre_lit, f.pre_lit, sizeof t.pre_lit);
+    struct CodeSink {
+        const XTable& t;
+        unsigned __int128 code = 0;
+        uint32_t nb = 0;
+        void put(uint32_t tok) {
+            if (nb < 100) code |= (unsigned __int128)(tok & 0xFFFFFFu) << nb;
+            nb += tok >> 24;
+        }
+        void lit(int id) { put(t.lit[id]); }
+        void tok(int g) { put(t.len_tok[g]); }
+    };
+    for (uint32_t key = 0; key < 4096; ++key) {
+        CodeSink cs{t};
+        int lead, lastp;
+        xunit_tokens(key & 63u, key >> 6, cs, lead, lastp);
+        if (lead < 0) continue;
+        const bool is_long = cs.nb > kLutMaxBits;
+        const uint64_t c = is_long ? 0 : (uint64_t)cs.code;
+        t.lut[key].x = (uint32_t)c;
+        t.lut[key].y = (uint32_t)((c >> 32) & 0x7FFu) | (is_long ? kLutLong : (cs.nb << 11)) | ((uint32_t)lead << 24) |
+                       ((uint32_t)lastp << 28);
+    }
+    return t;
 }
 
 struct ByteHist {

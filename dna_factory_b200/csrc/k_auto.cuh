@@ -109,7 +109,8 @@ __host__ __device__ inline void span_tokens_ref(const uint32_t m[4], uint32_t ca
 // ---- bit sinks ----
 // Staging sink: appends up to 64 bits at a time to the thread's private words stage[k * stride] (word-interleaved
 // across threads: conflict-free).  Branch-free: the three words an append can touch are stored every time.
-struct AStage {
+template <int CAP>
+struct AStageT {
     uint32_t* p;        // &stage[wi * stride + tid]
     uint32_t stride;    // in words
     uint32_t a0, nacc, wi;
@@ -117,7 +118,7 @@ struct AStage {
         const uint32_t w0 = a0 | (lo << nacc);
         const uint32_t w1 = __funnelshift_l(lo, hi, nacc);
         const uint32_t w2 = __funnelshift_l(hi, 0u, nacc);
-        if (wi < (uint32_t)kAStage) {
+        if (wi < (uint32_t)CAP) {
             p[0] = w0;
             p[stride] = w1;
             p[2 * stride] = w2;
@@ -138,6 +139,7 @@ struct AStage {
     }
     __device__ __forceinline__ uint32_t bits() const { return 32u * wi + nacc; }
 };
+using AStage = AStageT<kAStage>;
 
 // Direct sink (a span overflowed its staging area): ORs the bits into the zeroed output words.
 struct AEmit {

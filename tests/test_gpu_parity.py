@@ -133,13 +133,17 @@ def test_auto_kernel_dense_overrides_on_rare_rows(native, n, stride):
     from types import SimpleNamespace
     snps = [Snp(id=i + 1, chromosome='1', position=1000 * (i + 1), tuples=[("A", 1 - maf), ("C", 1.0)])
             for i, maf in enumerate([0.005, 0.01, 0.02, 0.25, 0.495, 0.005])]
+    # X rows take k_x: the same forced patterns on a rare row, a common row and a single-allele row
+    snps += [Snp(id=7, chromosome='X', position=5, tuples=[("A", 0.995), ("C", 1.0)]),
+             Snp(id=8, chromosome='X', position=6, tuples=[("A", 0.6), ("C", 1.0)]),
+             Snp(id=9, chromosome='X', position=7, tuples=[("G", 1.0)])]
     samples = []
     for i in range(n):
         ctl = i < n // 3
         d = None
         if not ctl:
             # every `stride`-th case carries every SNP; the last row only on a short burst of cases
-            d = {s.id: 0.5 for s in snps[:5]} if (i % stride == 0) else {}
+            d = {s.id: 0.5 for s in snps[:5] + snps[6:]} if (i % stride == 0) else {}
             if n // 2 <= i < n // 2 + 70:
                 d[6] = 0.5
         samples.append(Sample(family_id=i + 1, person_id=100001 + i, father_id=0, mother_id=0, sex=1 + (i & 1),
