@@ -127,7 +127,9 @@ struct dnaf_ctx {
     std::vector<BlockDesc> plan;
 
     cudaEvent_t ev[8] = {};
-    cudaStream_t side = nullptr;           // k_fused_text runs here, concurrently with k_fused_auto
+    cudaStream_t side = nullptr;           // k_fused_text runs here, concurrently with k_auto
+    cudaStream_t side2 = nullptr;          // k_x runs here
+    cudaEvent_t ev_join2 = nullptr;
     cudaStream_t copy = nullptr;           // D2H of pass i overlaps the kernels of pass i+1
     cudaStream_t tot = nullptr;            // 16-byte totals read-backs (never queued behind a data copy)
     struct OutBuf {                        // what must outlive a pass while the next one runs
@@ -1035,7 +1037,8 @@ int generate_impl(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t se
         const bool side_work = !c->tplan.empty() || !c->xplan.empty();
         if (side_work) {
             CU(c, cudaEventRecord(c->ev_fork, c->stream));
-            CU(c, cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+            if (!c->tplan.empty()) CU(c, cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+            if (!c->xplan.empty()) CU(c, cudaStreamWaitEvent(c->side2, c->ev_fork, 0));
         }
         if (!c->tplan.empty()) {
             if (!c->text_attr_done) {
@@ -1081,11 +1084,12 @@ int generate_impl(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t se
             xa.slots = c->d_slots.as<uint8_t>();
             xa.sizes = c->d_sizes.as<uint32_t>();
             xa.crcs = c->d_crcs.as<uint32_t>();
-            k_x<<<(uint32_t)c->xplan.size(), c->fused_threads, x_smem_bytes(c->fused_threads), c->side>>>(xa);
+            k_x<<<(uint32_t)c->xplan.size(), c->fused_threads, x_smem_bytes(c->fused_threads), c->side2>>>(xa);
             local.kernel_launches += 1;
             CU(c, cudaGetLastError());
         }
-        if (side_work) CU(c, cudaEventRecord(c->ev_join, c->side));
+        if (!c->tplan.empty()) CU(c, cudaEventRecord(c->ev_join, c->side));
+        if (!c->xplan.empty()) CU(c, cudaEventRecord(c->ev_join2, c->side2));
         if (!c->fplan.empty()) {
             AutoArgs fa;
             fa.sv = sample_view(c);
@@ -1111,7 +1115,8 @@ int generate_impl(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t se
             local.kernel_launches += 1;
             CU(c, cudaGetLastError());
         }
-        if (side_work) CU(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+        if (!c->tplan.empty()) CU(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+        if (!c->xplan.empty()) CU(c, cudaStreamWaitEvent(c->stream, c->ev_join2, 0));
         CU(c, cudaEventRecord(B.ev[4], c->stream));
         B.rows = r1 - r0;
         B.text = c->h_row_off[r1] - c->h_row_off[r0];
@@ -1183,6 +1188,7 @@ int dnaf_create(int device_ordinal, dnaf_ctx** out) {
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
         if ((e = cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, hi)) != cudaSuccess) return bail("cudaStreamCreate", e);
+        if ((e = cudaStreamCreateWithPriority(&c->side2, cudaStreamNonBlocking, hi)) != cudaSuccess) return bail("cudaStreamCreate", e);
     }
     if ((e = cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     if ((e = cudaStreamCreateWithFlags(&c->tot, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
@@ -1194,6 +1200,7 @@ int dnaf_create(int device_ordinal, dnaf_ctx** out) {
     }
     if ((e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&c->ev_join2, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     // CRC tables: byte table and x^(8k) mod P for k = 0..kBlk
     std::vector<uint32_t> tab(256), xp(kBlk + 1);
     for (uint32_t i = 0; i < 256; ++i) {
@@ -1221,6 +1228,8 @@ void dnaf_destroy(dnaf_ctx* c) {
     for (auto& ev : c->ev)
         if (ev) cudaEventDestroy(ev);
     if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
+    if (c->side2) { cudaStreamSynchronize(c->side2); cudaStreamDestroy(c->side2); }
+    if (c->ev_join2) cudaEventDestroy(c->ev_join2);
     if (c->copy) { cudaStreamSynchronize(c->copy); cudaStreamDestroy(c->copy); }
     if (c->tot) { cudaStreamSynchronize(c->tot); cudaStreamDestroy(c->tot); }
     for (auto& b : c->ob) {
