@@ -258,9 +258,18 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+    traffic, traffic_note = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            tr = json.load(f)
+        traffic = tr["dram_bytes_per_launch"]
+        traffic_note = "%s, one ncu --set full capture: %d-block launch emitting %.0f MB of text" % (
+            tr["kernel"], tr["blocks"], tr["text_bytes_of_that_launch"] / 1e6)
+    except Exception:
+        pass
     achieved = text_bytes / (stage_ms[dom] * 1e-3) / 1e9 if stage_ms[dom] > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": dom.replace("ms_", ""), "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None,
+                "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                 "algorithmic_bytes": "uncompressed VCF text bytes emitted (%.3f B/call)" % (text_bytes / max(1, sum(
                     s["calls"] for s in stats))),
