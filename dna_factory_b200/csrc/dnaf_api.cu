@@ -122,7 +122,13 @@ struct dnaf_ctx {
     DevBuf d_crctab, d_xpow8;
 
     // scratch
-    DevBuf d_plane0, d_plane1, d_text, d_slots, d_sizes, d_crcs, d_offsets, d_blocks, d_geno;
+    DevBuf d_plane0, d_plane1, d_text, d_blocks, d_geno;
+    struct SlotBuf {                       // block slots of a pass; two sets, so that the compaction of pass i (own
+        DevBuf slots, sizes, crcs;         // stream) overlaps the kernels of pass i+1
+        cudaEvent_t ev_free = nullptr;     // compaction that read this set has finished
+    } sbuf[2];
+    int sb = 0;
+    cudaStream_t comp = nullptr;           // k_size_partials + k_gather run here
     PinnedBuf h_blocks;
     std::vector<BlockDesc> plan;
 
@@ -797,9 +803,9 @@ int reserve_outputs(dnaf_ctx* c, dnaf_ctx::OutBuf& B, uint32_t nb_exact) {
     // whole multiples of 2048 blocks: passes of a job differ a little in block count, buffers must not be
     // re-allocated (cudaMalloc synchronises the device) every time one is a few blocks larger than the last
     const uint32_t nb = nb_exact > 256u ? (nb_exact + 2047u) / 2048u * 2048u : nb_exact;
-    CU(c, c->d_slots.reserve((size_t)nb * kSlot));
-    CU(c, c->d_sizes.reserve(nb * sizeof(uint32_t)));
-    CU(c, c->d_crcs.reserve(nb * sizeof(uint32_t)));
+    CU(c, c->sbuf[c->sb].slots.reserve((size_t)nb * kSlot));
+    CU(c, c->sbuf[c->sb].sizes.reserve(nb * sizeof(uint32_t)));
+    CU(c, c->sbuf[c->sb].crcs.reserve(nb * sizeof(uint32_t)));
     CU(c, B.d_totals.reserve((2 + 2 * (size_t)((nb + kGroup - 1u) / kGroup)) * sizeof(uint64_t)));   // state of k_size_partials / k_gather
     CU(c, B.d_out.reserve((size_t)nb * kSlot));
     CU(c, B.h_totals.reserve(2 * sizeof(uint64_t)));
@@ -819,28 +825,32 @@ int launch_generic(dnaf_ctx* c, dnaf_stats* st) {
     if (rc) return rc;
     k_bgzf_generic<<<nb, 256, sizeof(DeflateSmem), c->stream>>>(
         c->d_text.as<uint8_t>(), c->d_blocks.as<BlockDesc>(), c->gslot.empty() ? nullptr : c->d_gslot.as<uint32_t>(),
-        c->d_crctab.as<uint32_t>(), c->d_xpow8.as<uint32_t>(), c->d_slots.as<uint8_t>(), c->d_sizes.as<uint32_t>(),
-        c->d_crcs.as<uint32_t>());
+        c->d_crctab.as<uint32_t>(), c->d_xpow8.as<uint32_t>(), c->sbuf[c->sb].slots.as<uint8_t>(), c->sbuf[c->sb].sizes.as<uint32_t>(),
+        c->sbuf[c->sb].crcs.as<uint32_t>());
     if (st) st->kernel_launches += 1;
     CU(c, cudaGetLastError());
     return DNAF_OK;
 }
 
-// scan + compact the first nb slots into B.d_out; the totals follow on the copy stream
+// Compaction of the pass whose kernels were just queued on the main stream (ev[4] marks their end): sizes -> offsets ->
+// gather into B.d_out, on the compaction stream, so that it overlaps the next pass's kernels.  ev[5] = pass done.
 int close_pass(dnaf_ctx* c, dnaf_ctx::OutBuf& B, uint32_t nb, dnaf_stats* st) {
     B.nb = nb;
+    dnaf_ctx::SlotBuf& S = c->sbuf[c->sb];
+    CU(c, cudaStreamWaitEvent(c->comp, B.ev[4], 0));
     if (nb) {
         const uint32_t ntiles = (nb + kTile - 1u) / kTile, ngroups = (nb + kGroup - 1u) / kGroup;
-        k_size_partials<<<ngroups, kGroup, 0, c->stream>>>(c->d_sizes.as<uint32_t>(), c->d_crcs.as<uint32_t>(), nb,
-                                                           reinterpret_cast<unsigned long long*>(B.d_totals.p));
-        k_gather<<<ntiles, 256, 0, c->stream>>>(c->d_slots.as<uint8_t>(), kSlot, c->d_sizes.as<uint32_t>(), nb,
-                                                reinterpret_cast<unsigned long long*>(B.d_totals.p),
-                                                reinterpret_cast<unsigned long long*>(B.h_totals.p), B.d_out.as<uint8_t>());
+        k_size_partials<<<ngroups, kGroup, 0, c->comp>>>(S.sizes.as<uint32_t>(), S.crcs.as<uint32_t>(), nb,
+                                                         reinterpret_cast<unsigned long long*>(B.d_totals.p));
+        k_gather<<<ntiles, 256, 0, c->comp>>>(S.slots.as<uint8_t>(), kSlot, S.sizes.as<uint32_t>(), nb,
+                                              reinterpret_cast<unsigned long long*>(B.d_totals.p),
+                                              reinterpret_cast<unsigned long long*>(B.h_totals.p), B.d_out.as<uint8_t>());
         if (st) st->kernel_launches += 2;
-        if (st) st->kernel_launches += 1;
     }
-    CU(c, cudaEventRecord(B.ev[5], c->stream));
+    CU(c, cudaEventRecord(B.ev[5], c->comp));
+    CU(c, cudaEventRecord(S.ev_free, c->comp));
     CU(c, cudaGetLastError());
+    c->sb ^= 1;   // the next pass writes the other slot set
     return DNAF_OK;
 }
 
@@ -1009,6 +1019,7 @@ int generate_impl(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t se
         rc = reserve_outputs(c, B, c->pass_blocks);
         if (!rc) rc = reserve_stage(c, B);
         if (rc) return rc;
+        CU(c, cudaStreamWaitEvent(c->stream, c->sbuf[c->sb].ev_free, 0));   // compaction two passes ago read this slot set
         CU(c, cudaEventRecord(B.ev[0], c->stream));
         const uint32_t grows = (uint32_t)c->grow.size();
         if (grows) {
@@ -1057,9 +1068,9 @@ int generate_impl(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t se
             ta.row_base = c->row_base;
             ta.k0 = (uint32_t)seed;
             ta.k1 = (uint32_t)(seed >> 32);
-            ta.slots = c->d_slots.as<uint8_t>();
-            ta.sizes = c->d_sizes.as<uint32_t>();
-            ta.crcs = c->d_crcs.as<uint32_t>();
+            ta.slots = c->sbuf[c->sb].slots.as<uint8_t>();
+            ta.sizes = c->sbuf[c->sb].sizes.as<uint32_t>();
+            ta.crcs = c->sbuf[c->sb].crcs.as<uint32_t>();
             k_fused_text<<<(uint32_t)c->tplan.size(), c->text_threads, sizeof(TextSmem), c->side>>>(ta);
             local.kernel_launches += 1;
             CU(c, cudaGetLastError());
@@ -1081,9 +1092,9 @@ int generate_impl(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t se
             xa.row_base = c->row_base;
             xa.k0 = (uint32_t)seed;
             xa.k1 = (uint32_t)(seed >> 32);
-            xa.slots = c->d_slots.as<uint8_t>();
-            xa.sizes = c->d_sizes.as<uint32_t>();
-            xa.crcs = c->d_crcs.as<uint32_t>();
+            xa.slots = c->sbuf[c->sb].slots.as<uint8_t>();
+            xa.sizes = c->sbuf[c->sb].sizes.as<uint32_t>();
+            xa.crcs = c->sbuf[c->sb].crcs.as<uint32_t>();
             k_x<<<(uint32_t)c->xplan.size(), c->fused_threads, x_smem_bytes(c->fused_threads), c->side2>>>(xa);
             local.kernel_launches += 1;
             CU(c, cudaGetLastError());
@@ -1108,9 +1119,9 @@ int generate_impl(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t se
             fa.row_base = c->row_base;
             fa.k0 = (uint32_t)seed;
             fa.k1 = (uint32_t)(seed >> 32);
-            fa.slots = c->d_slots.as<uint8_t>();
-            fa.sizes = c->d_sizes.as<uint32_t>();
-            fa.crcs = c->d_crcs.as<uint32_t>();
+            fa.slots = c->sbuf[c->sb].slots.as<uint8_t>();
+            fa.sizes = c->sbuf[c->sb].sizes.as<uint32_t>();
+            fa.crcs = c->sbuf[c->sb].crcs.as<uint32_t>();
             k_auto<<<(uint32_t)c->fplan.size(), c->fused_threads, auto_smem_bytes(c->fused_threads), c->stream>>>(fa);
             local.kernel_launches += 1;
             CU(c, cudaGetLastError());
@@ -1191,6 +1202,9 @@ int dnaf_create(int device_ordinal, dnaf_ctx** out) {
         if ((e = cudaStreamCreateWithPriority(&c->side2, cudaStreamNonBlocking, hi)) != cudaSuccess) return bail("cudaStreamCreate", e);
     }
     if ((e = cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    if ((e = cudaStreamCreateWithFlags(&c->comp, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    for (auto& sbf : c->sbuf)
+        if ((e = cudaEventCreateWithFlags(&sbf.ev_free, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaStreamCreateWithFlags(&c->tot, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     for (auto& b : c->ob) {
         for (auto& ev : b.ev)
@@ -1231,6 +1245,9 @@ void dnaf_destroy(dnaf_ctx* c) {
     if (c->side2) { cudaStreamSynchronize(c->side2); cudaStreamDestroy(c->side2); }
     if (c->ev_join2) cudaEventDestroy(c->ev_join2);
     if (c->copy) { cudaStreamSynchronize(c->copy); cudaStreamDestroy(c->copy); }
+    if (c->comp) { cudaStreamSynchronize(c->comp); cudaStreamDestroy(c->comp); }
+    for (auto& sbf : c->sbuf)
+        if (sbf.ev_free) cudaEventDestroy(sbf.ev_free);
     if (c->tot) { cudaStreamSynchronize(c->tot); cudaStreamDestroy(c->tot); }
     for (auto& b : c->ob) {
         for (auto& ev : b.ev)
@@ -1623,14 +1640,17 @@ int dnaf_bgzf_compress(dnaf_ctx* c, const uint8_t* text, uint64_t n, int level, 
         int rc = reserve_outputs(c, B, (uint32_t)c->plan.size());
         if (!rc) rc = reserve_stage(c, B);
         if (rc) return rc;
-        for (int e = 0; e < 5; ++e) CU(c, cudaEventRecord(B.ev[e], c->stream));
+        CU(c, cudaStreamWaitEvent(c->stream, c->sbuf[c->sb].ev_free, 0));
+        for (int e = 0; e < 3; ++e) CU(c, cudaEventRecord(B.ev[e], c->stream));
         B.rows = 0;
         B.text = 0;
         B.gen = false;
         B.fused = false;
         B.generic_blocks = true;
         rc = launch_generic(c, &local);
-        if (!rc) rc = close_pass(c, B, (uint32_t)c->plan.size(), &local);
+        if (rc) return rc;
+        for (int e = 3; e < 5; ++e) CU(c, cudaEventRecord(B.ev[e], c->stream));   // ev[4]: the compaction stream waits for it
+        rc = close_pass(c, B, (uint32_t)c->plan.size(), &local);
         if (!rc) rc = queue_totals(c, B);
         if (!rc) rc = start_copy(c, B, s, &local);
         if (!rc) rc = finish_copy(c, B, s);
