@@ -303,7 +303,7 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src));
 }
 
-__global__ void __launch_bounds__(kFusedMaxThreads, 4) k_auto(const AutoArgs a) {
+__global__ void __maxnreg__(56) k_auto(const AutoArgs a) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const uint32_t tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31u, wid = tid >> 5;
     uint2* s_lut = reinterpret_cast<uint2*>(smem_raw);
