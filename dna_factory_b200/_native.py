@@ -37,7 +37,7 @@ class DnafError(RuntimeError):
 EXPORTS = ["dnaf_abi_version", "dnaf_last_error", "dnaf_create", "dnaf_destroy", "dnaf_set_stream",
            "dnaf_set_chunk_bytes", "dnaf_set_row_base", "dnaf_set_fused", "dnaf_set_samples", "dnaf_set_snps", "dnaf_set_overrides",
            "dnaf_plan", "dnaf_generate", "dnaf_generate_stream", "dnaf_generate_device", "dnaf_genotypes",
-           "dnaf_text", "dnaf_bgzf_compress", "dnaf_bgzf_bound", "dnaf_bgzf_eof", "dnaf_select_snps"]
+           "dnaf_text", "dnaf_bgzf_compress", "dnaf_bgzf_bound", "dnaf_bgzf_eof", "dnaf_select_snps", "dnaf_parse_snps_jsonl"]
 
 _lib = None
 
@@ -77,6 +77,9 @@ def load():
         "dnaf_bgzf_compress": (i32, [vp, u8p, u64, i32, u8p, u64, sp]),
         "dnaf_bgzf_bound": (u64, [u64]),
         "dnaf_bgzf_eof": (i32, [u8p]),
+        "dnaf_parse_snps_jsonl": (ctypes.c_int64, [ctypes.c_char_p, u64, u64, ctypes.POINTER(ctypes.c_int64),
+                                                   ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int64), u8p, u8p, f64p,
+                                                   ctypes.c_char_p, ctypes.c_uint32, u32p]),
         "dnaf_select_snps": (i32, [vp, u64, u64, ctypes.c_uint32, f64p, f64p, u8p, ctypes.c_uint32, f64p, i32, u32p, u8p, u8p,
                                    u32p, u8p, u8p]),
     }
@@ -255,6 +258,28 @@ class Engine:
         st = Stats()
         self._check(self._lib.dnaf_bgzf_compress(self._h, _u8(buf), n, level, _u8(out), bound, ctypes.byref(st)))
         return out[:st.bgzf_bytes].tobytes(), st.as_dict()
+
+
+def parse_snps_jsonl(data):
+    """Columns of an inflated snps.json (bytes), or None when a record needs the generic json path."""
+    lib = load()
+    cap = data.count(b"\n") + 1
+    ids = np.empty(cap, np.int64)
+    ci = np.empty(cap, np.int32)
+    pos = np.empty(cap, np.int64)
+    k = np.empty(cap, np.uint8)
+    nts = np.empty((cap, KMAX), np.uint8)
+    cum = np.empty((cap, KMAX), np.float64)
+    labels = ctypes.create_string_buffer(8 * 256)
+    nl = ctypes.c_uint32()
+    n = lib.dnaf_parse_snps_jsonl(data, len(data), cap, ids.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                                  ci.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                                  pos.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), _u8(k), _u8(nts),
+                                  cum.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), labels, 256, ctypes.byref(nl))
+    if n < 0:
+        return None
+    names = [labels.raw[8 * i:8 * i + 8].split(b"\0")[0].decode("latin-1") for i in range(nl.value)]
+    return dict(ids=ids[:n], chrom_idx=ci[:n], chrom_labels=names, position=pos[:n], n_alleles=k[:n], nts=nts[:n], cum=cum[:n])
 
 
 def bgzf_eof():

@@ -23,6 +23,7 @@
 #include "k_fused_text.cuh"
 #include "k_sample_format.cuh"
 #include "k_select.cuh"
+#include "snps_json.h"
 #include <map>
 #include <unordered_map>
 
@@ -1496,6 +1497,13 @@ int dnaf_select_snps(dnaf_ctx* c, uint64_t n, uint64_t seed, uint32_t n_chrom, c
     CU(c, cudaMemcpyAsync(alt, col_at(R, 4), n, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     return DNAF_OK;
+}
+
+int64_t dnaf_parse_snps_jsonl(const char* text, uint64_t n_bytes, uint64_t cap, int64_t* ids, int32_t* chrom_idx,
+                              int64_t* position, uint8_t* n_alleles, uint8_t* nts, double* cum, char* chrom_labels,
+                              uint32_t max_labels, uint32_t* n_labels) {
+    if (!text || !ids || !chrom_idx || !position || !n_alleles || !nts || !cum || !chrom_labels || !n_labels) return 0;
+    return snpsjson::parse(text, n_bytes, cap, ids, chrom_idx, position, n_alleles, nts, cum, chrom_labels, max_labels, n_labels);
 }
 
 uint64_t dnaf_bgzf_bound(uint64_t text_bytes) {

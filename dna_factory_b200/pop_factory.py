@@ -240,6 +240,10 @@ class PopulationFactory:
         print("Time to write snps file {:0.4f} seconds".format(time.time() - t0))
 
     def load_snps_file(self):
+        self.snp_table = SnpTable.read_json_gz_table(self.snps_path)   # native parser, columns only
+        if self.snp_table is not None:
+            self.snp_count = len(self.snp_table)
+            return
         self.ordered_snps = SnpTable.read_json_gz(self.snps_path)
         self.snp_count = len(self.ordered_snps)
         try:

@@ -278,6 +278,17 @@ class SnpTable:
         with gzip.open(path, "rt") as f:
             return [SNPTuples.from_json(line) for line in f]
 
+    @classmethod
+    def read_json_gz_table(cls, path):
+        """The same file straight into column form (native parser, no object per SNP); None when some record
+        does not fit the column form (string ids, multi-character alleles, ...): use read_json_gz then."""
+        with gzip.open(path, "rb") as f:
+            cols = _native.parse_snps_jsonl(f.read())
+        if cols is None:
+            return None
+        return cls(cols["ids"], cols["chrom_idx"], cols["chrom_labels"], cols["position"], cols["n_alleles"], cols["nts"],
+                   cols["cum"])
+
 
 class SnpFactory:
     """Frequency-CDF SNP selection (pop_factory.py:136-193).

@@ -124,6 +124,17 @@ int dnaf_select_snps(dnaf_ctx* ctx, uint64_t n_snps, uint64_t seed, uint32_t n_c
                      int sorted, uint32_t* order, uint8_t* chrom_idx, uint8_t* maf_bin, uint32_t* position,
                      uint8_t* ref, uint8_t* alt);
 
+/*
+ * load_snps_file (pop_factory.py:264-272) without a Python object per SNP: parses the inflated snps.json text
+ * (one SNPTuples.__str__ record per line, pop_factory.py:118-124) into columns.  Host code, no context needed.
+ * nts / cum are [cap][DNAF_KMAX] (unused entries 0 / 2.0; the order of "tuples" is kept); chrom_labels receives up to
+ * max_labels labels of <= 7 characters, 8 bytes each, in order of first appearance.  Returns the number of
+ * records, or -(line number) at the first record the column form cannot hold (the caller falls back to json.loads).
+ */
+int64_t dnaf_parse_snps_jsonl(const char* text, uint64_t n_bytes, uint64_t cap, int64_t* ids, int32_t* chrom_idx,
+                              int64_t* position, uint8_t* n_alleles, uint8_t* nts, double* cum, char* chrom_labels,
+                              uint32_t max_labels, uint32_t* n_labels);
+
 /* Sizes of rows [row_begin,row_end): exact text bytes and an upper bound on the BGZF bytes. */
 int dnaf_plan(dnaf_ctx* ctx, uint64_t row_begin, uint64_t row_end, uint64_t* text_bytes, uint64_t* bgzf_bound);
 

@@ -162,3 +162,32 @@ def test_threshold_is_exact_for_inclusive_compare():
             assert (cum >= U * 2.0 ** -32) == (U <= t), (cum, U)
     with pytest.raises(ValueError):
         host.threshold(-0.1)
+
+
+def test_native_snps_json_parser_matches_json_loads(tmp_path):
+    """dnaf_parse_snps_jsonl against SNPTuples.from_json (pop_factory.py:126-133) on the reference's own snps.json
+    (tests/golden/cli_small), on multi-allelic records, and its refusal of records outside the column form."""
+    import gzip
+    from dna_factory_b200 import _native, snp
+    from tests.cases import GOLDEN
+    raw = open(os.path.join(GOLDEN, "cli_small", "snps.json"), "rb").read()
+    cols = _native.parse_snps_jsonl(raw)
+    want = [snp.SNPTuples.from_json(line) for line in raw.decode().splitlines()]
+    assert cols is not None and len(cols["ids"]) == len(want)
+    tab = snp.SnpTable(cols["ids"], cols["chrom_idx"], cols["chrom_labels"], cols["position"], cols["n_alleles"], cols["nts"],
+                       cols["cum"])
+    assert [(s.id, s.chromosome, s.position, s.tuples) for s in tab.to_snps()] == \
+        [(s.id, s.chromosome, s.position, s.tuples) for s in want]
+    multi = (b'{"id": 7, "chromosome": "MT", "position": 5, "tuples": {"G": 0.4, "A": 0.7000000000000001, "T": 0.9, "C": 1.0}}\n'
+             b'{"id": 8, "chromosome": "X", "position": 0, "tuples": {"C": 1.0}}\n')
+    cols = _native.parse_snps_jsonl(multi)
+    assert cols["chrom_labels"] == ["MT", "X"] and list(cols["n_alleles"]) == [4, 1]
+    assert cols["cum"][0].tolist() == [0.4, 0.7000000000000001, 0.9, 1.0] and bytes(cols["nts"][0]) == b"GATC"
+    for bad in (b'{"id": "rs5", "chromosome": "1", "position": 1, "tuples": {"A": 1.0}}\n',       # string id
+                b'{"id": 5, "chromosome": "1", "position": 1, "tuples": {"AT": 1.0}}\n',          # multi-character allele
+                b'{"id": 5, "chromosome": "1", "position": 1}\n'):                                # no tuples
+        assert _native.parse_snps_jsonl(bad) is None
+    path = tmp_path / "snps.json.gz"
+    with gzip.open(path, "wb") as f:
+        f.write(raw)
+    assert len(snp.SnpTable.read_json_gz_table(str(path))) == len(want)
