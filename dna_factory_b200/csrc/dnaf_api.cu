@@ -303,7 +303,7 @@ uint32_t raw_crc(const uint8_t* p, size_t n, const uint32_t* tab) {
     return c;
 }
 
-constexpr int kVariants = 12;  // tables per MAF bucket: auto+prefix, auto, (class x {prefix, no prefix}) for k_fused_text, X+prefix, X for k_fused_x
+constexpr int kVariants = 12;  // tables per MAF bucket: [0,1] k_auto with / without prefix, [2..9] k_fused_text (class x {prefix, no prefix}), [10,11] k_x
 
 // Called from set_snps: bucket every row by its first threshold, remember which prefix bytes occur.
 int prepare_buckets(dnaf_ctx* c, const uint8_t* kk, const uint32_t* thr) {
@@ -620,7 +620,7 @@ void build_segments(dnaf_ctx* c) {
     }
 }
 
-// 0 = generic three-kernel path, 1 = k_fused_auto, 2 = k_fused_text, 3 = k_fused_x
+// 0 = generic three-kernel path, 1 = k_auto, 2 = k_fused_text, 3 = k_x
 inline int row_kind(const dnaf_ctx* c, uint64_t r, const uint8_t* hk) {
     if (!c->fused || !c->fused_ok || c->h_plen[r] < 1 || c->h_plen[r] > 64 || c->n == 0) return 0;
     if (c->body[c->h_cls[r]] < kFusedMinRowBytes) return 0;

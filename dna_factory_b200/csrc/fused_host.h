@@ -1,10 +1,10 @@
-// Host-side set-up for the fused kernel: static Huffman codes per minor-allele-frequency bucket, their
-// serialized deflate dynamic-block headers, and the CRC tables the mask-domain checksum needs.
+// Host-side set-up for the fused kernels: static Huffman codes per minor-allele-frequency bucket, their
+// serialized deflate dynamic-block headers, the token lookup tables and CRC helper tables.
 //
-// The codes are built from token statistics obtained by running the kernel's own tokeniser
-// (tokenize_cells, k_fused.cuh) over Bernoulli(maf) masks from a fixed-seed generator, which is the model
-// the reference's row loop samples from (pop_factory.py:477-494).  Every symbol a block can need gets a
-// code (add-one smoothing), so any mask pattern -- including forced-minor cells -- stays encodable.
+// The codes are built from token statistics obtained by running the kernels' own span grammars
+// (span_tokens_ref, xspan_tokens_ref, tokenize_words) over Bernoulli(maf) masks from a fixed-seed generator,
+// which is the model the reference's row loop samples from (pop_factory.py:477-494).  Every symbol a block can
+// need gets a code (add-one smoothing), so any mask pattern -- including forced-minor cells -- stays encodable.
 #pragma once
 #include <algorithm>
 #include <cstdint>
@@ -172,49 +172,7 @@ struct HistSink {
     uint64_t nlen[29] = {0};
     void lit(int id) { nlit[id]++; }
     void match(int l) { nlen[len_index(l)]++; }
-    void gap_lit(int gap, int odd, int bit) {
-        if (gap == 1) lit(odd ? kLitSlash : kLitTab);
-        else if (gap) match(gap);
-        lit(bit);
-    }
-    void gap_tok(int gap, int id) {
-        if (gap) match(gap);
-        lit(id);
-    }
-    void fused3(int gap, int id_a, int id_b, int id) {
-        if (gap >= 3) match(gap);
-        else {
-            if (gap >= 1) lit(id_a);
-            if (gap == 2) lit(id_b);
-        }
-        lit(id);
-    }
 };
-
-// Token statistics of `blocks` full segments (255 spans of 64 cells) of Bernoulli(p_minor) alleles.
-inline HistSink simulate(double p_minor, int blocks) {
-    HistSink h;
-    uint64_t st = 0x9E3779B97F4A7C15ull ^ (uint64_t)(p_minor * 1e9);
-    auto next = [&]() {
-        st ^= st << 13; st ^= st >> 7; st ^= st << 17;
-        return st;
-    };
-    const uint64_t thr = (uint64_t)(std::min(p_minor, 0.999999) * 18446744073709551615.0);
-    for (int b = 0; b < blocks; ++b) {
-        uint32_t carry = 0;
-        for (int sp = 0; sp < 255; ++sp) {
-            uint32_t m[4];
-            for (int w = 0; w < 4; ++w) {
-                uint32_t v = 0;
-                for (int i = 0; i < 32; ++i) v |= (uint32_t)(next() < thr) << i;
-                m[w] = v;
-            }
-            tokenize_cells(m, carry, sp > 0, 64, false, h);
-            carry = m[3] >> 30;
-        }
-    }
-    return h;
-}
 
 // Codes for cell literals, all match lengths, EOB (+ prefix byte literals when `prefix_hist`) from token counts
 // gathered over `blocks` blocks.
@@ -245,8 +203,6 @@ inline FusedTable finish_cell_table(const HistSink& h, uint64_t blocks, const ui
         t.len_tok[len] = ((c & 0xFFFFFFu) | ((uint32_t)(len - kLenBase[ci]) << cl)) | ((cl + ex + 1u) << 24);
     }
     for (int i = 0; i < 5; ++i) t.lit[i] = lc[lit_byte[i]];
-    t.len_tok[1] = lc['\t'];   // a 1-byte gap is the separator before the allele: '\t' before slot 0, '/' before slot 1
-    t.len_tok[2] = lc['/'];
     t.eob = lc[256];
     for (int c = 0; c < 256; ++c) t.pre_lit[c] = lc[c];
     BitString hdr = dynamic_header(ll);
@@ -254,11 +210,6 @@ inline FusedTable finish_cell_table(const HistSink& h, uint64_t blocks, const ui
     for (size_t i = 0; i < hdr.words.size() && i < 62; ++i) t.hdr[i] = hdr.words[i];
     if (hdr.words.size() > 62) t.hdr_bits = 0xFFFFFFFFu;  // caller treats as "no table" (cannot happen: < 1 KiB)
     return t;
-}
-
-inline FusedTable make_table(double p_minor, const uint64_t* prefix_hist) {
-    const int kBlocks = 4;
-    return finish_cell_table(simulate(p_minor, kBlocks), kBlocks, prefix_hist);
 }
 
 // ---- k_auto (k_auto.cuh): token statistics under its span grammar, code tables and the byte LUT ----

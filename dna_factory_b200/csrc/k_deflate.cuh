@@ -377,45 +377,7 @@ __global__ void __launch_bounds__(256, 1) k_bgzf_generic(const uint8_t* __restri
     }
 }
 
-// Exclusive scan of block sizes (single CTA; block counts per pass are at most a few hundred thousand).
-__global__ void __launch_bounds__(1024) k_scan_sizes(const uint32_t* __restrict__ sizes, uint32_t nb,
-                                                    uint64_t* __restrict__ offsets, const uint32_t* __restrict__ crcs,
-                                                    uint64_t* __restrict__ totals /* [0]=bytes [1]=crc xor */) {
-    __shared__ uint64_t wsum[32];
-    __shared__ uint32_t wxor[32];
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
-    const uint32_t per = (nb + 1023u) / 1024u;
-    const uint32_t b0 = min(nb, tid * per), b1 = min(nb, b0 + per);
-    uint64_t sum = 0;
-    uint32_t x = 0;
-    for (uint32_t i = b0; i < b1; ++i) { sum += sizes[i]; x ^= crcs[i]; }
-    uint64_t v = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint64_t u = __shfl_up_sync(0xFFFFFFFFu, v, o);
-        if (lane >= (uint32_t)o) v += u;
-    }
-    x = warp_xor(x);
-    if (lane == 31u) { wsum[wid] = v; wxor[wid] = x; }
-    __syncthreads();
-    if (wid == 0) {
-        const uint64_t w = wsum[lane];
-        uint64_t s2 = w;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint64_t u = __shfl_up_sync(0xFFFFFFFFu, s2, o);
-            if (lane >= (uint32_t)o) s2 += u;
-        }
-        wsum[lane] = s2 - w;  // exclusive prefix of the warp totals
-        const uint32_t xx = warp_xor(wxor[lane]);
-        if (lane == 31u) { totals[0] = s2; totals[1] = xx; }
-    }
-    __syncthreads();
-    uint64_t run = wsum[wid] + v - sum;
-    for (uint32_t i = b0; i < b1; ++i) { offsets[i] = run; run += sizes[i]; }
-}
-
-// Gathers slot b into the contiguous stream at offsets[b].
+// Copies one block's bytes from its slot to its place in the contiguous stream.
 __device__ __forceinline__ void copy_block(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint32_t n,
                                            uint32_t tid, uint32_t nthr) {
     // 16-byte stores to the destination; the source is read as ALIGNED 16-byte words too and shifted into place
@@ -443,12 +405,6 @@ __device__ __forceinline__ void copy_block(const uint8_t* __restrict__ src, uint
         d16[i] = make_uint4(o[0], o[1], o[2], o[3]);
     }
     for (uint32_t i = head + body * 16u + tid; i < n; i += nthr) dst[i] = src[i];
-}
-
-__global__ void __launch_bounds__(256) k_compact(const uint8_t* __restrict__ slots, uint32_t slot_stride,
-                                                const uint32_t* __restrict__ sizes, const uint64_t* __restrict__ offsets,
-                                                uint8_t* __restrict__ out) {
-    copy_block(slots + (uint64_t)blockIdx.x * slot_stride + kSlotLead, out + offsets[blockIdx.x], sizes[blockIdx.x], threadIdx.x, blockDim.x);
 }
 
 // Scan + gather without any inter-CTA dependency:
