@@ -37,7 +37,8 @@ class DnafError(RuntimeError):
 EXPORTS = ["dnaf_abi_version", "dnaf_last_error", "dnaf_create", "dnaf_destroy", "dnaf_set_stream",
            "dnaf_set_chunk_bytes", "dnaf_set_row_base", "dnaf_set_fused", "dnaf_set_samples", "dnaf_set_snps", "dnaf_set_overrides",
            "dnaf_plan", "dnaf_generate", "dnaf_generate_stream", "dnaf_generate_device", "dnaf_genotypes",
-           "dnaf_text", "dnaf_bgzf_compress", "dnaf_bgzf_bound", "dnaf_bgzf_eof", "dnaf_select_snps", "dnaf_parse_snps_jsonl"]
+           "dnaf_text", "dnaf_bgzf_compress", "dnaf_bgzf_bound", "dnaf_bgzf_eof", "dnaf_select_snps", "dnaf_parse_snps_jsonl", "dnaf_format_prefixes",
+           "dnaf_format_snps_jsonl"]
 
 _lib = None
 
@@ -80,6 +81,10 @@ def load():
         "dnaf_parse_snps_jsonl": (ctypes.c_int64, [ctypes.c_char_p, u64, u64, ctypes.POINTER(ctypes.c_int64),
                                                    ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int64), u8p, u8p, f64p,
                                                    ctypes.c_char_p, ctypes.c_uint32, u32p]),
+        "dnaf_format_prefixes": (u64, [u64, ctypes.POINTER(ctypes.c_int32), ctypes.c_char_p, ctypes.POINTER(ctypes.c_int64),
+                                       ctypes.POINTER(ctypes.c_int64), u8p, u8p, u8p, u64p]),
+        "dnaf_format_snps_jsonl": (u64, [u64, ctypes.POINTER(ctypes.c_int32), ctypes.c_char_p, ctypes.POINTER(ctypes.c_int64),
+                                         ctypes.POINTER(ctypes.c_int64), u8p, u8p, u32p, ctypes.c_char_p, u32p, u8p]),
         "dnaf_select_snps": (i32, [vp, u64, u64, ctypes.c_uint32, f64p, f64p, u8p, ctypes.c_uint32, f64p, i32, u32p, u8p, u8p,
                                    u32p, u8p, u8p]),
     }
@@ -280,6 +285,58 @@ def parse_snps_jsonl(data):
         return None
     names = [labels.raw[8 * i:8 * i + 8].split(b"\0")[0].decode("latin-1") for i in range(nl.value)]
     return dict(ids=ids[:n], chrom_idx=ci[:n], chrom_labels=names, position=pos[:n], n_alleles=k[:n], nts=nts[:n], cum=cum[:n])
+
+
+def _label_block(labels):
+    buf = bytearray(8 * len(labels))
+    for i, name in enumerate(labels):
+        b = name.encode("latin-1")
+        if not 0 < len(b) <= 7:
+            raise ValueError("chromosome label %r does not fit 7 bytes" % name)
+        buf[8 * i:8 * i + len(b)] = b
+    return bytes(buf)
+
+
+def format_prefixes(ids, chrom_idx, labels, position, n_alleles, nts):
+    """Row prefixes (pop_factory.py:503-507) of a column-form SNP table -> (bytes array incl. one pad byte, offsets)."""
+    lib = load()
+    n = len(ids)
+    ids = np.ascontiguousarray(ids, np.int64)
+    pos = np.ascontiguousarray(position, np.int64)
+    ci = np.ascontiguousarray(chrom_idx, np.int32)
+    k = np.ascontiguousarray(n_alleles, np.uint8)
+    nt = np.ascontiguousarray(nts, np.uint8)
+    out = np.empty(n * 72 + 16, np.uint8)
+    off = np.empty(n + 1, np.uint64)
+    i64p = ctypes.POINTER(ctypes.c_int64)
+    used = lib.dnaf_format_prefixes(n, ci.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), _label_block(labels),
+                                    pos.ctypes.data_as(i64p), ids.ctypes.data_as(i64p), _u8(k), _u8(nt), _u8(out),
+                                    off.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)))
+    out[used] = 0
+    return out[:used + 1], off
+
+
+def format_snps_jsonl(ids, chrom_idx, labels, position, n_alleles, nts, cum):
+    """snps.json text (SNPTuples.__str__ per line, pop_factory.py:118-124) of a column-form SNP table -> bytes."""
+    import json
+    lib = load()
+    n = len(ids)
+    ids = np.ascontiguousarray(ids, np.int64)
+    pos = np.ascontiguousarray(position, np.int64)
+    ci = np.ascontiguousarray(chrom_idx, np.int32)
+    k = np.ascontiguousarray(n_alleles, np.uint8)
+    nt = np.ascontiguousarray(nts, np.uint8)
+    uniq, inv = np.unique(np.ascontiguousarray(cum, np.float64), return_inverse=True)
+    strs = [json.dumps(float(v)).encode() + b"\0" for v in uniq]     # Python's float repr, as json.dumps prints it
+    roff = np.zeros(len(strs) + 1, np.uint32)
+    roff[1:] = np.cumsum([len(x) for x in strs])
+    ridx = np.ascontiguousarray(inv.reshape(n, KMAX), np.uint32)
+    out = np.empty(n * (96 + KMAX * (8 + max(len(x) for x in strs))) + 16, np.uint8)
+    i64p, u32p = ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_uint32)
+    used = lib.dnaf_format_snps_jsonl(n, ci.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), _label_block(labels),
+                                      pos.ctypes.data_as(i64p), ids.ctypes.data_as(i64p), _u8(k), _u8(nt),
+                                      ridx.ctypes.data_as(u32p), b"".join(strs), roff.ctypes.data_as(u32p), _u8(out))
+    return out[:used].tobytes()
 
 
 def bgzf_eof():

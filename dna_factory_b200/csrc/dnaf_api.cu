@@ -1506,6 +1506,17 @@ int64_t dnaf_parse_snps_jsonl(const char* text, uint64_t n_bytes, uint64_t cap, 
     return snpsjson::parse(text, n_bytes, cap, ids, chrom_idx, position, n_alleles, nts, cum, chrom_labels, max_labels, n_labels);
 }
 
+uint64_t dnaf_format_prefixes(uint64_t n, const int32_t* chrom_idx, const char* labels, const int64_t* position,
+                              const int64_t* ids, const uint8_t* n_alleles, const uint8_t* nts, char* out, uint64_t* off) {
+    return snpsfmt::prefixes(n, chrom_idx, labels, position, ids, n_alleles, nts, out, off);
+}
+
+uint64_t dnaf_format_snps_jsonl(uint64_t n, const int32_t* chrom_idx, const char* labels, const int64_t* position,
+                                const int64_t* ids, const uint8_t* n_alleles, const uint8_t* nts, const uint32_t* repr_idx,
+                                const char* reprs, const uint32_t* repr_off, char* out) {
+    return snpsfmt::jsonl(n, chrom_idx, labels, position, ids, n_alleles, nts, repr_idx, reprs, repr_off, out);
+}
+
 uint64_t dnaf_bgzf_bound(uint64_t text_bytes) {
     // every block carries <= kBlk bytes of text and at most 26 + 5 bytes of framing beyond them;
     // row-aligned cutting can leave blocks partly filled, so count blocks generously

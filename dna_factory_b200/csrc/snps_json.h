@@ -134,3 +134,82 @@ inline int64_t parse(const char* text, size_t n_bytes, uint64_t cap, int64_t* id
 
 }  // namespace snpsjson
 }  // namespace dnaf
+
+// ---- emitters (host code): the row prefixes of pop_factory.py:503-507 and the lines of SNPTuples.__str__ ----
+namespace dnaf {
+namespace snpsfmt {
+
+inline char* put_uint(char* p, uint64_t v) {
+    char tmp[24];
+    int n = 0;
+    do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+    while (n) *p++ = tmp[--n];
+    return p;
+}
+
+inline char* put_str(char* p, const char* s) {
+    while (*s) *p++ = *s++;
+    return p;
+}
+
+// "%s\t%i\trs%s\t%s\t%s\t40\tPASS\t.\tGT\t" % (chromosome, position, id, ref, alt_alleles())  -- pop_factory.py:503-507
+// with alt_alleles() of pop_factory.py:111-116: tuples[1] for K == 2, the REF itself for K == 1, comma-joined tuples[1:] else.
+// labels: 8 bytes per chromosome label, NUL padded.  Returns bytes written; off[r] .. off[r+1] delimit row r.
+inline uint64_t prefixes(uint64_t n, const int32_t* chrom_idx, const char* labels, const int64_t* position, const int64_t* ids,
+                         const uint8_t* k, const uint8_t* nts, char* out, uint64_t* off) {
+    char* p = out;
+    for (uint64_t r = 0; r < n; ++r) {
+        off[r] = (uint64_t)(p - out);
+        p = put_str(p, labels + 8 * chrom_idx[r]);
+        *p++ = '\t';
+        p = put_uint(p, (uint64_t)position[r]);
+        p = put_str(p, "\trs");
+        p = put_uint(p, (uint64_t)ids[r]);
+        *p++ = '\t';
+        *p++ = (char)nts[4 * r];
+        *p++ = '\t';
+        if (k[r] == 1) *p++ = (char)nts[4 * r];
+        else
+            for (int j = 1; j < k[r]; ++j) {
+                if (j > 1) *p++ = ',';
+                *p++ = (char)nts[4 * r + j];
+            }
+        p = put_str(p, "\t40\tPASS\t.\tGT\t");
+    }
+    off[n] = (uint64_t)(p - out);
+    return (uint64_t)(p - out);
+}
+
+// {"id": 329, "chromosome": "1", "position": 1798996, "tuples": {"T": 0.98, "A": 1.0}}\n   -- json.dumps of
+// pop_factory.py:118-124.  Floats are printed by the caller (Python's repr): repr_idx[r*4+j] indexes the table of
+// NUL-terminated strings `reprs` (repr_off[i] = start of string i).
+inline uint64_t jsonl(uint64_t n, const int32_t* chrom_idx, const char* labels, const int64_t* position, const int64_t* ids,
+                      const uint8_t* k, const uint8_t* nts, const uint32_t* repr_idx, const char* reprs, const uint32_t* repr_off,
+                      char* out) {
+    char* p = out;
+    for (uint64_t r = 0; r < n; ++r) {
+        p = put_str(p, "{\"id\": ");
+        p = put_uint(p, (uint64_t)ids[r]);
+        p = put_str(p, ", \"chromosome\": \"");
+        p = put_str(p, labels + 8 * chrom_idx[r]);
+        p = put_str(p, "\", \"position\": ");
+        p = put_uint(p, (uint64_t)position[r]);
+        if (k[r]) {
+            p = put_str(p, ", \"tuples\": {");
+            for (int j = 0; j < k[r]; ++j) {
+                if (j) p = put_str(p, ", ");
+                *p++ = '"';
+                *p++ = (char)nts[4 * r + j];
+                p = put_str(p, "\": ");
+                p = put_str(p, reprs + repr_off[repr_idx[4 * r + j]]);
+            }
+            *p++ = '}';
+        }
+        *p++ = '}';
+        *p++ = '\n';
+    }
+    return (uint64_t)(p - out);
+}
+
+}  // namespace snpsfmt
+}  // namespace dnaf

@@ -198,8 +198,19 @@ class SnpTable:
         return np.where(col < self.n_alleles[:, None], t, np.uint32(0xFFFFFFFF)).astype(np.uint32)
 
     def prefix_bytes(self):
-        """Row leads "%s\\t%i\\trs%s\\t%s\\t%s\\t40\\tPASS\\t.\\tGT\\t" (pop_factory.py:503-507), vectorised:
-        fixed-width fields with a validity mask, flattened row-major."""
+        """Row leads "%s\\t%i\\trs%s\\t%s\\t%s\\t40\\tPASS\\t.\\tGT\\t" (pop_factory.py:503-507): the native formatter
+        (dnaf_format_prefixes), or the numpy one for chromosome labels longer than 7 bytes."""
+        S = len(self)
+        if S == 0:
+            return np.zeros(1, np.uint8), np.zeros(1, np.uint64)
+        if np.any(self.position < 0) or np.any(self.ids < 0):
+            raise ValueError("negative position / id")
+        if all(0 < len(c.encode("latin-1")) <= 7 for c in self.chrom_labels):
+            return _native.format_prefixes(self.ids, self.chrom_idx, self.chrom_labels, self.position, self.n_alleles, self.nts)
+        return self.prefix_bytes_numpy()
+
+    def prefix_bytes_numpy(self):
+        """The same bytes, vectorised in numpy: fixed-width fields with a validity mask, flattened row-major."""
         S = len(self)
         if S == 0:
             return np.zeros(1, np.uint8), np.zeros(1, np.uint64)
@@ -258,6 +269,15 @@ class SnpTable:
 
     # ---- snps.json.gz (pop_factory.py:118-133,258-272) -------------------------------------------
     def write_json_gz(self, path, compresslevel=5):
+        if len(self) and all(0 < len(c.encode("latin-1")) <= 7 and c.isalnum() for c in self.chrom_labels):
+            data = _native.format_snps_jsonl(self.ids, self.chrom_idx, self.chrom_labels, self.position, self.n_alleles,
+                                             self.nts, self.cum)
+            with gzip.open(path, "wb", compresslevel=compresslevel) as f:
+                f.write(data)
+            return
+        self.write_json_gz_python(path, compresslevel)
+
+    def write_json_gz_python(self, path, compresslevel=5):
         with gzip.open(path, "wt", compresslevel=compresslevel) as f:
             reprs = {}
             for r in range(len(self)):

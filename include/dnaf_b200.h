@@ -135,6 +135,20 @@ int64_t dnaf_parse_snps_jsonl(const char* text, uint64_t n_bytes, uint64_t cap, 
                               int64_t* position, uint8_t* n_alleles, uint8_t* nts, double* cum, char* chrom_labels,
                               uint32_t max_labels, uint32_t* n_labels);
 
+/*
+ * Host-side formatters for column-form SNP tables (no context needed; `labels` = 8 bytes per chromosome label).
+ * dnaf_format_prefixes: the row leads "%s\t%i\trs%s\t%s\t%s\t40\tPASS\t.\tGT\t" of pop_factory.py:503-507 (ALT as
+ *   SNPTuples.alt_alleles, pop_factory.py:111-116) into `out` (caller sizes it: <= 64 + 8 bytes per row), offsets in
+ *   off[n+1]; returns the bytes written.  Ids and positions must be non-negative.
+ * dnaf_format_snps_jsonl: the snps.json lines of SNPTuples.__str__ (pop_factory.py:118-124); floats come from the
+ *   caller's table of Python reprs (repr_idx[r*4+j] -> reprs + repr_off[...], NUL-terminated).  Returns bytes written.
+ */
+uint64_t dnaf_format_prefixes(uint64_t n, const int32_t* chrom_idx, const char* labels, const int64_t* position,
+                              const int64_t* ids, const uint8_t* n_alleles, const uint8_t* nts, char* out, uint64_t* off);
+uint64_t dnaf_format_snps_jsonl(uint64_t n, const int32_t* chrom_idx, const char* labels, const int64_t* position,
+                                const int64_t* ids, const uint8_t* n_alleles, const uint8_t* nts, const uint32_t* repr_idx,
+                                const char* reprs, const uint32_t* repr_off, char* out);
+
 /* Sizes of rows [row_begin,row_end): exact text bytes and an upper bound on the BGZF bytes. */
 int dnaf_plan(dnaf_ctx* ctx, uint64_t row_begin, uint64_t row_end, uint64_t* text_bytes, uint64_t* bgzf_bound);
 

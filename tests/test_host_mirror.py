@@ -191,3 +191,24 @@ def test_native_snps_json_parser_matches_json_loads(tmp_path):
     with gzip.open(path, "wb") as f:
         f.write(raw)
     assert len(snp.SnpTable.read_json_gz_table(str(path))) == len(want)
+
+
+def test_native_formatters_match_the_python_ones(tmp_path):
+    """dnaf_format_prefixes / dnaf_format_snps_jsonl against the numpy / json.dumps implementations they replace
+    (row lead of pop_factory.py:503-507, SNPTuples.__str__ of pop_factory.py:118-124), incl. K = 1, 3, 4 records."""
+    import gzip
+    from dna_factory_b200 import snp
+    from tests.cases import synth_case
+    case = synth_case(3, 400, seed=9, chroms=['1', '12', 'X', 'Y', 'MT'], exotic=True)
+    tab = snp.SnpTable.from_snps(case.snps).sorted()
+    a, b = tab.prefix_bytes(), tab.prefix_bytes_numpy()
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    want = b"".join(("%s\t%i\trs%s\t%s\t%s\t40\tPASS\t.\tGT\t" % (s.chromosome, s.position, s.id, s.ref_allele_tuple()[0],
+                                                                  s.alt_alleles() if len(s.tuples) > 1 else s.tuples[0][0])
+                     ).encode() for s in tab.to_snps())
+    assert a[0][:-1].tobytes() == want
+    tab.write_json_gz(str(tmp_path / "a.gz"))
+    tab.write_json_gz_python(str(tmp_path / "b.gz"))
+    got = gzip.open(tmp_path / "a.gz", "rb").read()
+    assert got == gzip.open(tmp_path / "b.gz", "rb").read()
+    assert got.decode().splitlines() == [str(s) for s in tab.to_snps()]
