@@ -105,7 +105,7 @@ def test_oracle_vs_cuda_synthetic(native, n, s, seed):
 
 
 @pytest.mark.parametrize("n,s,seed", [(4096, 12, 31), (4097, 12, 32), (4160, 8, 33), (16256, 5, 34), (16257, 5, 35),
-                                      (16320, 4, 36), (20000, 24, 37), (33000, 6, 38)])
+                                      (16320, 4, 36), (20000, 24, 37), (33000, 6, 38), (100003, 5, 39)])
 def test_fused_kernel_vs_oracle_and_generic(native, n, s, seed):
     """The fused sample+format+deflate kernel (autosome rows of >= 4096 samples) against the oracle text and
     against the three-kernel path; block streams may differ, decompressed bytes may not."""
