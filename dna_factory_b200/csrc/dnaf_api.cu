@@ -295,7 +295,11 @@ int ensure_layout(dnaf_ctx* c) {
 
 // ------------------------------------------------------------------------------------------------
 // Fused-path set-up: MAF buckets -> static Huffman tables; CRC helper tables; template CRCs per segment.
-constexpr uint32_t kFusedMinRowBytes = 16384;  // shorter rows are packed several to a block by the generic path
+#ifndef DNAF_MIN_FUSED
+#define DNAF_MIN_FUSED 4096
+#endif
+constexpr uint32_t kFusedMinRowBytes = DNAF_MIN_FUSED;  // rows of at least 1024 diploid samples get a block of their own (fused kernels);
+                                                         // shorter ones are packed several to a block by the generic path
 
 uint32_t raw_crc(const uint8_t* p, size_t n, const uint32_t* tab) {
     uint32_t c = 0;
