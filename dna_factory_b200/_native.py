@@ -36,7 +36,7 @@ class DnafError(RuntimeError):
 # every symbol include/dnaf_b200.h declares (tests check the built library exports all of them)
 EXPORTS = ["dnaf_abi_version", "dnaf_last_error", "dnaf_create", "dnaf_destroy", "dnaf_set_stream",
            "dnaf_set_chunk_bytes", "dnaf_set_row_base", "dnaf_set_fused", "dnaf_set_samples", "dnaf_set_snps", "dnaf_set_overrides",
-           "dnaf_plan", "dnaf_generate", "dnaf_generate_stream", "dnaf_generate_device", "dnaf_genotypes",
+           "dnaf_plan", "dnaf_generate", "dnaf_generate_stream", "dnaf_generate_fd", "dnaf_generate_device", "dnaf_genotypes",
            "dnaf_text", "dnaf_bgzf_compress", "dnaf_bgzf_bound", "dnaf_bgzf_eof", "dnaf_select_snps", "dnaf_parse_snps_jsonl", "dnaf_format_prefixes",
            "dnaf_format_snps_jsonl"]
 
@@ -72,6 +72,7 @@ def load():
         "dnaf_plan": (i32, [vp, u64, u64, u64p, u64p]),
         "dnaf_generate": (i32, [vp, u64, u64, u64, i32, i32, u8p, u64, sp]),
         "dnaf_generate_stream": (i32, [vp, u64, u64, u64, i32, i32, SINK_FN, vp, sp]),
+        "dnaf_generate_fd": (i32, [vp, u64, u64, u64, i32, i32, i32, sp]),
         "dnaf_generate_device": (i32, [vp, u64, u64, u64, i32, i32, sp]),
         "dnaf_genotypes": (i32, [vp, u64, u64, u64, u8p, u64]),
         "dnaf_text": (i32, [vp, u64, u64, u64, u8p, u64, u64p]),
@@ -233,6 +234,12 @@ class Engine:
         if err:
             raise err[0]
         self._check(rc)
+        return st.as_dict()
+
+    def generate_fd(self, row_begin, row_end, seed, fd, level=6, rng_mode=0):
+        """Same stream, written to an open file descriptor by the library itself; returns stats dict."""
+        st = Stats()
+        self._check(self._lib.dnaf_generate_fd(self._h, row_begin, row_end, seed, rng_mode, level, fd, ctypes.byref(st)))
         return st.as_dict()
 
     def generate_device(self, row_begin, row_end, seed, level=6, rng_mode=0):

@@ -7,7 +7,10 @@
 // Work is cut into passes of at most `chunk_bytes` of uncompressed text; each pass is
 //   sample -> (overrides) -> format -> BGZF encode -> scan -> compact -> D2H -> sink      (generic path)
 // or the fused kernel (k_fused.cuh) followed by scan -> compact -> D2H -> sink.
+#include <unistd.h>
+
 #include <algorithm>
+#include <cerrno>
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
@@ -759,10 +762,21 @@ struct Sink {
     uint64_t cap = 0, used = 0;
     bool device_only = false;
     bool pinned = false;     // buf is page-locked host memory
+    int fd = -1;             // file descriptor mode: write() straight from the page-locked staging buffer
 };
 
 int deliver(dnaf_ctx* c, Sink& s, const uint8_t* data, uint64_t n) {
-    if (s.fn) {
+    if (s.fd >= 0) {
+        uint64_t done = 0;
+        while (done < n) {
+            const ssize_t w = ::write(s.fd, data + done, (size_t)std::min<uint64_t>(n - done, 1u << 30));
+            if (w < 0) {
+                if (errno == EINTR) continue;
+                return fail(c, DNAF_E_SINK, "write to file descriptor %d failed: %s", s.fd, strerror(errno));
+            }
+            done += (uint64_t)w;
+        }
+    } else if (s.fn) {
         if (s.fn(s.user, data, n) != 0) return fail(c, DNAF_E_SINK, "sink callback failed");
     } else if (s.buf) {
         if (s.used + n > s.cap) return fail(c, DNAF_E_SPACE, "output buffer too small: need more than %llu bytes",
@@ -1564,6 +1578,15 @@ int dnaf_generate_stream(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint
     Sink s;
     s.fn = sink;
     s.user = user;
+    return generate_impl(c, row_begin, row_end, seed, rng_mode, level, s, stats);
+}
+
+int dnaf_generate_fd(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t seed, int rng_mode, int level, int fd,
+                     dnaf_stats* stats) {
+    if (!c) return DNAF_E_ARG;
+    if (fd < 0) return fail(c, DNAF_E_ARG, "bad file descriptor");
+    Sink s;
+    s.fd = fd;
     return generate_impl(c, row_begin, row_end, seed, rng_mode, level, s, stats);
 }
 

@@ -331,7 +331,7 @@ class PopulationFactory:
                 eng.set_snps(**arrays)
                 eng.set_overrides(orow, osamp)
                 file.flush()
-                st = eng.generate_stream(0, n_rows, seed, file._handle.write, level=level)
+                st = eng.generate_fd(0, n_rows, seed, file._handle.fileno(), level=level)   # the handle was just flushed
                 self.stats.append(st)
             finally:
                 if own:

@@ -163,6 +163,10 @@ int dnaf_generate(dnaf_ctx* ctx, uint64_t row_begin, uint64_t row_end, uint64_t 
                   uint8_t* out, uint64_t out_cap, dnaf_stats* stats);
 int dnaf_generate_stream(dnaf_ctx* ctx, uint64_t row_begin, uint64_t row_end, uint64_t seed, int rng_mode,
                          int level, dnaf_sink_fn sink, void* user, dnaf_stats* stats);
+/* Same work, every piece written to an open file descriptor (the ordered `file.write(line)` loop of
+ * pop_factory.py:438-469 without a trip through the interpreter); the caller flushes its own buffers first. */
+int dnaf_generate_fd(dnaf_ctx* ctx, uint64_t row_begin, uint64_t row_end, uint64_t seed, int rng_mode, int level,
+                     int fd, dnaf_stats* stats);
 /* Same work, output left in (and then discarded from) device memory: kernel-only timing. */
 int dnaf_generate_device(dnaf_ctx* ctx, uint64_t row_begin, uint64_t row_end, uint64_t seed, int rng_mode,
                          int level, dnaf_stats* stats);

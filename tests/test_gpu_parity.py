@@ -213,6 +213,22 @@ def test_stream_sink_and_chunking(native):
     assert x == st["crc_xor"]
 
 
+def test_fd_sink_writes_the_same_stream(native, tmp_path):
+    """dnaf_generate_fd (the library writes the blocks itself) against the buffer sink: identical bytes on disk."""
+    case = synth_case(6000, 40, seed=12)
+    eng = _engine(native, case, chunk=4 << 20)
+    want, st0 = eng.generate(0, 40, case.seed, level=2)
+    path = tmp_path / "rows.bgzf"
+    with open(path, "wb") as f:
+        f.write(b"HEAD")
+        f.flush()
+        st = eng.generate_fd(0, 40, case.seed, f.fileno(), level=2)
+    assert path.read_bytes() == b"HEAD" + want
+    assert st["bgzf_bytes"] == len(want) and st["crc_xor"] == st0["crc_xor"]
+    with pytest.raises(native[0].DnafError):
+        eng.generate_fd(0, 40, case.seed, 10 ** 6, level=2)      # not an open descriptor
+
+
 def test_errors_are_loud(native):
     _native, host = native
     eng = _native.Engine(0)
