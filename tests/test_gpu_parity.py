@@ -284,3 +284,44 @@ def test_snp_selection_device_feeds_generation(native):
     host.configure(eng, case.samples, snps)
     blob, st = eng.generate(0, len(snps), 77, level=2)
     assert oracle.bgzf_decompress(blob)[0] == want
+
+
+def test_full_size_c2_properties(native):
+    """BASELINE config C2 at full size (10 000 + 10 000 samples x 5 000 000 SNPs = 1e11 calls, 395 GB of text), output
+    left on the device: size-independent properties.  Row ranges concatenate (bytes add up, the xor of the block
+    CRC32s -- the checksum of checksums -- composes), the counts match the plan, and windows anywhere in the
+    population decompress to the oracle's rows."""
+    import bench
+    from oracle import oracle
+    _native, host = native
+    S = bench.TOTAL_SNPS
+    sex, ctl, table, orow, osamp = bench.synth_population(S, 0, window=S)
+    eng = _native.Engine(0)
+    eng.set_samples(sex, ctl)
+    eng.set_snps(**table.device_arrays())
+    eng.set_overrides(orow, osamp)
+    text_bytes, _ = eng.plan(0, S)
+    whole = eng.generate_device(0, S, bench.PHILOX_SEED, level=2)
+    assert whole["rows"] == S and whole["calls"] == S * len(sex) == 10 ** 11
+    assert whole["text_bytes"] == text_bytes > 3.9e11
+    cuts = [0, 1, 777_777, S // 2, S - 3, S]
+    parts = [eng.generate_device(a, b, bench.PHILOX_SEED, level=2) for a, b in zip(cuts, cuts[1:])]
+    assert sum(p["text_bytes"] for p in parts) == text_bytes
+    assert sum(p["calls"] for p in parts) == whole["calls"]
+    x = 0
+    for p in parts:
+        x ^= p["crc_xor"]
+    assert x == whole["crc_xor"]          # CRC32 of a block depends on its bytes only; blocks are cut on row boundaries
+    # windows: first rows, the X/Y tail of the sorted list, and somewhere in the middle -- against the oracle
+    from types import SimpleNamespace
+    fam = [SimpleNamespace(sex=int(s), is_control=bool(c), deleterious_snps=None if c else {}, person_id=i)
+           for i, (s, c) in enumerate(zip(sex, ctl))]
+    for lo in (0, 2_345_678, S - 40):
+        hi = lo + 40
+        blob, st = eng.generate(lo, hi, bench.PHILOX_SEED, level=2)
+        flat = oracle.flatten(fam, [table.snp(r) for r in range(lo, hi)])
+        sel = (orow >= lo) & (orow < hi)
+        flat["over_row"] = (orow[sel] - lo).astype(np.uint64)
+        flat["over_sample"] = osamp[sel]
+        want, _ = oracle.rows_from_flat(flat, bench.PHILOX_SEED, lo, n_threads=8)
+        assert oracle.bgzf_decompress(blob)[0] == want.tobytes()
