@@ -168,6 +168,8 @@ struct dnaf_ctx {
     std::vector<uint64_t> goff;
     uint64_t gen_text_bytes = 0;
     uint32_t pass_blocks = 0;
+    uint32_t slot_stride = kSlot;          // per pass: the longest block's text + room for framing, rounded to 256
+    uint64_t pass_text = 0;
     uint32_t fused_threads = 256;
     int cur_ob = 0;
     std::map<std::pair<uint64_t, uint64_t>, FusedTable> table_cache;
@@ -753,6 +755,15 @@ void plan_pass(dnaf_ctx* c, uint64_t r0, uint64_t r1, const uint8_t* hk) {
     }
     c->gen_text_bytes = gtext;
     c->pass_blocks = slot;
+    // Slot stride of the pass: the longest block's text (a stored block is the worst case: text + 5) plus the slot
+    // lead, BGZF framing, the zero-fill / copy overrun of the kernels (< 64 bytes), rounded up to 256.
+    uint32_t longest = 0;
+    for (const FusedDesc& d : c->fplan) longest = std::max(longest, 4u * d.ncells + 66u);           // prefix <= 64, +1 lead, +1
+    for (const FusedDesc& d : c->xplan) longest = std::max(longest, 4u * d.ncells + 66u);
+    for (const TextDesc& d : c->tplan) longest = std::max(longest, d.nbytes + 66u);
+    for (const BlockDesc& b : c->plan) longest = std::max(longest, b.len);
+    c->slot_stride = std::min<uint32_t>(kSlot, (longest + 128u + 255u) & ~255u);
+    c->pass_text = c->h_row_off[r1] - c->h_row_off[r0];
 }
 
 struct Sink {
@@ -818,15 +829,15 @@ int reserve_stage(dnaf_ctx* c, dnaf_ctx::OutBuf& B) {
     return DNAF_OK;
 }
 
-int reserve_outputs(dnaf_ctx* c, dnaf_ctx::OutBuf& B, uint32_t nb_exact) {
+int reserve_outputs(dnaf_ctx* c, dnaf_ctx::OutBuf& B, uint32_t nb_exact, uint64_t text_bytes) {
     // whole multiples of 2048 blocks: passes of a job differ a little in block count, buffers must not be
     // re-allocated (cudaMalloc synchronises the device) every time one is a few blocks larger than the last
     const uint32_t nb = nb_exact > 256u ? (nb_exact + 2047u) / 2048u * 2048u : nb_exact;
-    CU(c, c->sbuf[c->sb].slots.reserve((size_t)nb * kSlot));
+    CU(c, c->sbuf[c->sb].slots.reserve((size_t)nb * c->slot_stride + 256));
     CU(c, c->sbuf[c->sb].sizes.reserve(nb * sizeof(uint32_t)));
     CU(c, c->sbuf[c->sb].crcs.reserve(nb * sizeof(uint32_t)));
     CU(c, B.d_totals.reserve((2 + 2 * (size_t)((nb + kGroup - 1u) / kGroup)) * sizeof(uint64_t)));   // state of k_size_partials / k_gather
-    CU(c, B.d_out.reserve((size_t)nb * kSlot));
+    CU(c, B.d_out.reserve(text_bytes + (size_t)nb * 64 + 256));   // worst case: every block stored
     CU(c, B.h_totals.reserve(2 * sizeof(uint64_t)));
     if (!c->attr_done) {
         CU(c, cudaFuncSetAttribute(k_bgzf_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DeflateSmem)));
@@ -844,7 +855,7 @@ int launch_generic(dnaf_ctx* c, dnaf_stats* st) {
     if (rc) return rc;
     k_bgzf_generic<<<nb, 256, sizeof(DeflateSmem), c->stream>>>(
         c->d_text.as<uint8_t>(), c->d_blocks.as<BlockDesc>(), c->gslot.empty() ? nullptr : c->d_gslot.as<uint32_t>(),
-        c->d_crctab.as<uint32_t>(), c->d_xpow8.as<uint32_t>(), c->sbuf[c->sb].slots.as<uint8_t>(), c->sbuf[c->sb].sizes.as<uint32_t>(),
+        c->d_crctab.as<uint32_t>(), c->d_xpow8.as<uint32_t>(), c->sbuf[c->sb].slots.as<uint8_t>(), c->slot_stride, c->sbuf[c->sb].sizes.as<uint32_t>(),
         c->sbuf[c->sb].crcs.as<uint32_t>());
     if (st) st->kernel_launches += 1;
     CU(c, cudaGetLastError());
@@ -861,7 +872,7 @@ int close_pass(dnaf_ctx* c, dnaf_ctx::OutBuf& B, uint32_t nb, dnaf_stats* st) {
         const uint32_t ntiles = (nb + kTile - 1u) / kTile, ngroups = (nb + kGroup - 1u) / kGroup;
         k_size_partials<<<ngroups, kGroup, 0, c->comp>>>(S.sizes.as<uint32_t>(), S.crcs.as<uint32_t>(), nb,
                                                          reinterpret_cast<unsigned long long*>(B.d_totals.p));
-        k_gather<<<ntiles, 256, 0, c->comp>>>(S.slots.as<uint8_t>(), kSlot, S.sizes.as<uint32_t>(), nb,
+        k_gather<<<ntiles, 256, 0, c->comp>>>(S.slots.as<uint8_t>(), c->slot_stride, S.sizes.as<uint32_t>(), nb,
                                               reinterpret_cast<unsigned long long*>(B.d_totals.p),
                                               reinterpret_cast<unsigned long long*>(B.h_totals.p), B.d_out.as<uint8_t>());
         if (st) st->kernel_launches += 2;
@@ -1035,7 +1046,7 @@ int generate_impl(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t se
         plan_pass(c, r0, r1, c->h_k.data());
         const auto t_plan1 = std::chrono::steady_clock::now();
         c->cur_ob = cur;
-        rc = reserve_outputs(c, B, c->pass_blocks);
+        rc = reserve_outputs(c, B, c->pass_blocks, c->pass_text);
         if (!rc) rc = reserve_stage(c, B);
         if (rc) return rc;
         CU(c, cudaStreamWaitEvent(c->stream, c->sbuf[c->sb].ev_free, 0));   // compaction two passes ago read this slot set
@@ -1088,6 +1099,7 @@ int generate_impl(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t se
             ta.k0 = (uint32_t)seed;
             ta.k1 = (uint32_t)(seed >> 32);
             ta.slots = c->sbuf[c->sb].slots.as<uint8_t>();
+            ta.slot_stride = c->slot_stride;
             ta.sizes = c->sbuf[c->sb].sizes.as<uint32_t>();
             ta.crcs = c->sbuf[c->sb].crcs.as<uint32_t>();
             k_fused_text<<<(uint32_t)c->tplan.size(), c->text_threads, sizeof(TextSmem), c->side>>>(ta);
@@ -1112,6 +1124,7 @@ int generate_impl(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t se
             xa.k0 = (uint32_t)seed;
             xa.k1 = (uint32_t)(seed >> 32);
             xa.slots = c->sbuf[c->sb].slots.as<uint8_t>();
+            xa.slot_stride = c->slot_stride;
             xa.sizes = c->sbuf[c->sb].sizes.as<uint32_t>();
             xa.crcs = c->sbuf[c->sb].crcs.as<uint32_t>();
             k_x<<<(uint32_t)c->xplan.size(), c->fused_threads, x_smem_bytes(c->fused_threads), c->side2>>>(xa);
@@ -1139,6 +1152,7 @@ int generate_impl(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t se
             fa.k0 = (uint32_t)seed;
             fa.k1 = (uint32_t)(seed >> 32);
             fa.slots = c->sbuf[c->sb].slots.as<uint8_t>();
+            fa.slot_stride = c->slot_stride;
             fa.sizes = c->sbuf[c->sb].sizes.as<uint32_t>();
             fa.crcs = c->sbuf[c->sb].crcs.as<uint32_t>();
             k_auto<<<(uint32_t)c->fplan.size(), c->fused_threads, auto_smem_bytes(c->fused_threads), c->stream>>>(fa);
@@ -1683,7 +1697,8 @@ int dnaf_bgzf_compress(dnaf_ctx* c, const uint8_t* text, uint64_t n, int level, 
             c->plan.push_back({o, (uint32_t)std::min<uint64_t>(kBlk, piece - o), 0});
         dnaf_ctx::OutBuf& B = c->ob[0];
         c->cur_ob = 0;
-        int rc = reserve_outputs(c, B, (uint32_t)c->plan.size());
+        c->slot_stride = kSlot;
+        int rc = reserve_outputs(c, B, (uint32_t)c->plan.size(), piece);
         if (!rc) rc = reserve_stage(c, B);
         if (rc) return rc;
         CU(c, cudaStreamWaitEvent(c->stream, c->sbuf[c->sb].ev_free, 0));

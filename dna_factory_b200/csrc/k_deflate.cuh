@@ -279,7 +279,8 @@ __global__ void __launch_bounds__(256, 1) k_bgzf_generic(const uint8_t* __restri
                                                         const uint32_t* __restrict__ slot_idx,
                                                         const uint32_t* __restrict__ g_crctab,
                                                         const uint32_t* __restrict__ g_xpow8, uint8_t* __restrict__ slots,
-                                                        uint32_t* __restrict__ sizes, uint32_t* __restrict__ crcs) {
+                                                        uint32_t slot_stride, uint32_t* __restrict__ sizes,
+                                                        uint32_t* __restrict__ crcs) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     DeflateSmem& s = *reinterpret_cast<DeflateSmem*>(smem_raw);
     const uint32_t tid = threadIdx.x;
@@ -342,7 +343,7 @@ __global__ void __launch_bounds__(256, 1) k_bgzf_generic(const uint8_t* __restri
     const bool stored = payload > n + 5u || payload > kSlot - 26u;
 
     const uint32_t slot_no = slot_idx ? slot_idx[blockIdx.x] : blockIdx.x;
-    uint8_t* slot = slots + (uint64_t)slot_no * kSlot + kSlotLead;  // see dnaf_device.cuh
+    uint8_t* slot = slots + (uint64_t)slot_no * slot_stride + kSlotLead;  // see dnaf_device.cuh
     uint32_t out_payload;
     if (!stored) {
         // -- pass 3: emit

@@ -208,6 +208,7 @@ struct XArgs {
     uint64_t row_base;
     uint32_t k0, k1;
     uint8_t* slots;
+    uint32_t slot_stride;      // bytes per output slot of this pass (>= the longest block's text + 96)
     uint32_t* sizes;
     uint32_t* crcs;
 };
@@ -511,7 +512,7 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 4) k_x(const XArgs a) {
     const uint32_t payload = (data_bits + 7u) / 8u;
     const uint32_t out_words = (data_bits + 31u) / 32u;
     const bool stored = payload > n + 5u;
-    uint8_t* blk = a.slots + (uint64_t)d.slot * kSlot + kSlotLead;
+    uint8_t* blk = a.slots + (uint64_t)d.slot * a.slot_stride + kSlotLead;
     uint32_t* words = reinterpret_cast<uint32_t*>(blk + 18);  // 16-byte aligned
 
     uint32_t out_payload;
