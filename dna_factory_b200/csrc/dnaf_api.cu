@@ -186,6 +186,9 @@ struct dnaf_ctx {
     // k_auto (k_auto.cuh): code tables + byte LUTs per (bucket, starts-row), CRC move tables, per-row prefix CRCs
     DevBuf d_atables, d_etab2, d_mtab, d_mtail, d_mpre, d_xinit, d_pre_crc;
     DevBuf d_xtables, d_mspan, d_mpre_x;   // k_x (k_x.cuh)
+    DevBuf d_bucket, d_ovr_first, d_seginfo;   // implicit block descriptors of all-autosome passes (k_auto.cuh)
+    std::vector<uint32_t> h_other;          // [S+1]: rows before r that do NOT take k_auto
+    bool implicit_pass = false;
     std::map<std::pair<uint64_t, uint64_t>, XTable> xtable_cache;
     std::vector<uint32_t> h_mspan, h_mpre_x;
     std::map<std::pair<uint64_t, uint64_t>, AutoTable> atable_cache;
@@ -265,6 +268,7 @@ SnpView snp_view(const dnaf_ctx* c) {
 
 void build_segments(dnaf_ctx* c);
 int ensure_tables(dnaf_ctx* c);
+int ensure_implicit(dnaf_ctx* c);
 
 // Text offset of every row (prefix + class body), host and device copies.
 int ensure_layout(dnaf_ctx* c) {
@@ -294,6 +298,9 @@ int ensure_layout(dnaf_ctx* c) {
     rc = ensure_tables(c);
     if (rc) return rc;
     trace("tables ensured", 0);
+    rc = ensure_implicit(c);
+    if (rc) return rc;
+    trace("implicit descriptors ready", 0);
     c->layout_ok = true;
     return DNAF_OK;
 }
@@ -638,6 +645,35 @@ inline int row_kind(const dnaf_ctx* c, uint64_t r, const uint8_t* hk) {
     return 2;
 }
 inline bool row_is_fused(const dnaf_ctx* c, uint64_t r, const uint8_t* hk) { return row_kind(c, r, hk) != 0; }
+
+// What k_auto needs to derive its block descriptors itself when a pass holds autosome rows only: which rows those
+// are (host: prefix count of the others), the bucket and first override of every row, the segment table.
+int ensure_implicit(dnaf_ctx* c) {
+    c->h_other.assign(c->S + 1, 0);
+    uint32_t others = 0;
+    for (uint64_t r = 0; r < c->S; ++r) {
+        c->h_other[r] = others;
+        others += row_kind(c, r, c->h_k.data()) != 1;
+    }
+    c->h_other[c->S] = others;
+    if (!c->fused_ok || c->S == 0 || others == c->S) return DNAF_OK;
+    std::vector<uint32_t> first(c->S + 1);
+    size_t o = 0;
+    for (uint64_t r = 0; r <= c->S; ++r) {
+        while (o < c->h_orow.size() && c->h_orow[o] < r) ++o;
+        first[r] = (uint32_t)o;
+    }
+    std::vector<uint32_t> seg;
+    for (size_t sg = 0; sg + 1 < c->h_seg_cell0.size(); ++sg) {
+        seg.push_back(c->h_seg_cell0[sg]);
+        seg.push_back(c->h_seg_cell0[sg + 1] - c->h_seg_cell0[sg]);
+        seg.push_back(c->h_seg_crc[sg]);
+    }
+    int rc = upload(c, c->d_bucket, c->h_bucket.data(), c->h_bucket.size(), false);
+    if (!rc) rc = upload(c, c->d_ovr_first, first.data(), first.size(), false);
+    if (!rc) rc = upload(c, c->d_seginfo, seg.data(), seg.size());
+    return rc;
+}
 
 // BGZF block plan of one pass (rows [r0,r1)): fused segments and generic blocks, slots in row order.
 void plan_pass(dnaf_ctx* c, uint64_t r0, uint64_t r1, const uint8_t* hk) {
@@ -1043,7 +1079,20 @@ int generate_impl(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t se
         const uint64_t r1 = next_chunk_end(c, r0, row_end, std::max<uint64_t>(c->chunk_bytes >> std::max(0, 3 - npass), 4096));
         dnaf_ctx::OutBuf& B = c->ob[cur];
         const auto t_plan0 = std::chrono::steady_clock::now();
-        plan_pass(c, r0, r1, c->h_k.data());
+        c->implicit_pass = c->fused_ok && c->h_other[r1] == c->h_other[r0] && !c->h_seg_crc.empty();
+        if (c->implicit_pass) {   // autosome rows only: k_auto derives its descriptors, the host plans nothing
+            c->fplan.clear(); c->xplan.clear(); c->tplan.clear(); c->plan.clear(); c->gslot.clear(); c->grow.clear();
+            c->goff.clear(); c->olocal.clear(); c->osub.clear();
+            c->gen_text_bytes = 0;
+            const uint32_t nseg = (uint32_t)c->h_seg_crc.size();
+            c->pass_blocks = (uint32_t)(r1 - r0) * nseg;
+            uint32_t longest = 0;
+            for (uint32_t sg = 0; sg < nseg; ++sg) longest = std::max(longest, 4u * (c->h_seg_cell0[sg + 1] - c->h_seg_cell0[sg]) + 66u);
+            c->slot_stride = std::min<uint32_t>(kSlot, (longest + 128u + 255u) & ~255u);
+            c->pass_text = c->h_row_off[r1] - c->h_row_off[r0];
+        } else {
+            plan_pass(c, r0, r1, c->h_k.data());
+        }
         const auto t_plan1 = std::chrono::steady_clock::now();
         c->cur_ob = cur;
         rc = reserve_outputs(c, B, c->pass_blocks, c->pass_text);
@@ -1133,11 +1182,16 @@ int generate_impl(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t se
         }
         if (!c->tplan.empty()) CU(c, cudaEventRecord(c->ev_join, c->side));
         if (!c->xplan.empty()) CU(c, cudaEventRecord(c->ev_join2, c->side2));
-        if (!c->fplan.empty()) {
+        if (!c->fplan.empty() || c->implicit_pass) {
             AutoArgs fa;
             fa.sv = sample_view(c);
             fa.nv = snp_view(c);
-            fa.desc = c->d_fdesc.as<FusedDesc>();
+            fa.desc = c->implicit_pass ? nullptr : c->d_fdesc.as<FusedDesc>();
+            fa.row0 = r0;
+            fa.nseg = (uint32_t)c->h_seg_crc.size();
+            fa.seginfo = c->d_seginfo.as<uint32_t>();
+            fa.bucket = c->d_bucket.as<uint16_t>();
+            fa.ovr_first = c->d_ovr_first.as<uint32_t>();
             fa.tables = c->d_atables.as<AutoTable>();
             fa.etab = c->d_etab2.as<uint32_t>();
             fa.mtab = c->d_mtab.as<uint32_t>();
@@ -1155,7 +1209,8 @@ int generate_impl(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t se
             fa.slot_stride = c->slot_stride;
             fa.sizes = c->sbuf[c->sb].sizes.as<uint32_t>();
             fa.crcs = c->sbuf[c->sb].crcs.as<uint32_t>();
-            k_auto<<<(uint32_t)c->fplan.size(), c->fused_threads, auto_smem_bytes(c->fused_threads), c->stream>>>(fa);
+            k_auto<<<c->implicit_pass ? c->pass_blocks : (uint32_t)c->fplan.size(), c->fused_threads, auto_smem_bytes(c->fused_threads),
+                     c->stream>>>(fa);
             local.kernel_launches += 1;
             CU(c, cudaGetLastError());
         }
@@ -1166,7 +1221,7 @@ int generate_impl(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t se
         B.text = c->h_row_off[r1] - c->h_row_off[r0];
         B.gen = grows != 0;
         B.generic_blocks = !c->plan.empty();
-        B.fused = !c->fplan.empty() || !c->tplan.empty() || !c->xplan.empty();
+        B.fused = c->implicit_pass || !c->fplan.empty() || !c->tplan.empty() || !c->xplan.empty();
         rc = close_pass(c, B, c->pass_blocks, &local);
         if (rc) return rc;
         if (g_trace) {
@@ -1321,6 +1376,7 @@ int dnaf_set_row_base(dnaf_ctx* c, uint64_t row_base) {
 int dnaf_set_fused(dnaf_ctx* c, int enable) {
     if (!c) return DNAF_E_ARG;
     c->fused = enable ? 1 : 0;
+    c->layout_ok = false;   // which rows take which kernel changes
     return DNAF_OK;
 }
 
@@ -1446,6 +1502,7 @@ int dnaf_set_overrides(dnaf_ctx* c, uint64_t P, const uint64_t* rows, const uint
     if (!rc) rc = upload(c, c->d_osamp, samples, P);
     if (rc) return rc;
     c->P = P;
+    c->layout_ok = false;   // the per-row override index is part of the layout
     return DNAF_OK;
 }
 

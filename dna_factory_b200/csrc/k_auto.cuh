@@ -47,7 +47,13 @@ static_assert(kATabWords % 4 == 0 && sizeof(AutoTable) % 16 == 0, "AutoTable mus
 struct AutoArgs {
     SampleView sv;
     SnpView nv;
-    const FusedDesc* desc;
+    const FusedDesc* desc;     // one per block, or NULL: every row of the pass is an autosome row and block b is
+                               // segment b % nseg of row row0 + b / nseg (no host planning, nothing to upload)
+    uint64_t row0;
+    uint32_t nseg;
+    const uint32_t* seginfo;   // [nseg][3]: first cell, cells, template CRC of the segment
+    const uint16_t* bucket;    // per row: MAF bucket (tables 2*bucket, 2*bucket + 1)
+    const uint32_t* ovr_first; // [rows + 1]: first override of every row
     const AutoTable* tables;
     const uint32_t* etab;      // [16][256] span-local CRC contributions of mask bytes, measured to ONE BYTE BEFORE the span's cell end
     const uint32_t* mtab;      // [254][4][256] multiply by x^(8*256*j)
@@ -316,7 +322,21 @@ __global__ void __maxnreg__(56) k_auto(const AutoArgs a) {
     const uint32_t* s_lits = s_len + 264;
     const uint32_t* s_hdr = s_len + 274;
 
-    const FusedDesc d = a.desc[blockIdx.x];
+    FusedDesc d;
+    if (a.desc) {
+        d = a.desc[blockIdx.x];
+    } else {
+        const uint32_t rl = blockIdx.x / a.nseg, sg = blockIdx.x - rl * a.nseg;
+        d.row = a.row0 + rl;
+        d.cell0 = __ldg(&a.seginfo[3u * sg]);
+        d.ncells = __ldg(&a.seginfo[3u * sg + 1u]);
+        d.body_crc = __ldg(&a.seginfo[3u * sg + 2u]);
+        d.slot = blockIdx.x;
+        d.flags = (sg == 0u ? 1u : 0u) | (sg + 1u == a.nseg ? 2u : 0u);
+        d.ovr_first = __ldg(&a.ovr_first[d.row]);
+        d.ovr_count = __ldg(&a.ovr_first[d.row + 1]) - d.ovr_first;
+        d.table = 2u * __ldg(&a.bucket[d.row]) + (sg == 0u ? 0u : 1u);
+    }
     const AutoTable* __restrict__ tb = a.tables + d.table;
     {   // code tables of this block's bucket -> shared memory, asynchronously: they are needed after the draws
         const uint4* src = reinterpret_cast<const uint4*>(tb->lut);
