@@ -1290,7 +1290,11 @@ int dnaf_create(int device_ordinal, dnaf_ctx** out) {
         if ((e = cudaStreamCreateWithPriority(&c->side2, cudaStreamNonBlocking, hi)) != cudaSuccess) return bail("cudaStreamCreate", e);
     }
     if ((e = cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
-    if ((e = cudaStreamCreateWithFlags(&c->comp, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    {   // high priority: the compaction of pass i must not queue behind the blocks of pass i+1's kernels
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if ((e = cudaStreamCreateWithPriority(&c->comp, cudaStreamNonBlocking, hi)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    }
     for (auto& sbf : c->sbuf)
         if ((e = cudaEventCreateWithFlags(&sbf.ev_free, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaStreamCreateWithFlags(&c->tot, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
