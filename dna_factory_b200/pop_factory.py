@@ -354,10 +354,13 @@ class PopulationFactory:
                     eng.set_samples(sex, ctl)
                     eng.set_snps(**arrays)
                     eng.set_overrides(orow, osamp)
-                    self.stats.append(eng.generate_stream(bounds[g], bounds[g + 1], seed, spools[g].write, level=level))
+                    # rank 0's stream goes straight behind the header; the others spool and are appended in rank order
+                    fd = file._handle.fileno() if g == 0 else spools[g].fileno()
+                    self.stats.append(eng.generate_fd(bounds[g], bounds[g + 1], seed, fd, level=level))
             except BaseException as e:  # noqa: re-raised on the caller's thread
                 errors.append(e)
 
+        file.flush()   # the header blocks must be in the file before rank 0 writes behind them
         threads = [threading.Thread(target=run, args=(g,)) for g in range(gpus)]
         for t in threads:
             t.start()
@@ -365,14 +368,15 @@ class PopulationFactory:
             t.join()
         if errors:
             raise errors[0]
-        file.flush()
-        for sp in spools:
+        for sp in spools[1:]:
             sp.seek(0)
             while True:
                 buf = sp.read(1 << 24)
                 if not buf:
                     break
                 file._handle.write(buf)
+        file._handle.flush()
+        for sp in spools:
             sp.close()
 
     # ------------------------------------------------------------------------------------------ deleterious sets
