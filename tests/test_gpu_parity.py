@@ -1,5 +1,6 @@
 """GPU parity tests (run on the B200 box with -m gpu): the CUDA path, called through the C ABI,
 against the committed reference goldens and against the CPU oracle on seeded synthetic inputs."""
+import os
 import zlib
 
 import numpy as np
@@ -325,3 +326,14 @@ def test_full_size_c2_properties(native):
         flat["over_sample"] = osamp[sel]
         want, _ = oracle.rows_from_flat(flat, bench.PHILOX_SEED, lo, n_threads=8)
         assert oracle.bgzf_decompress(blob)[0] == want.tobytes()
+
+
+def test_randomised_shapes_soak():
+    """A short run of scripts/fuzz_parity.py (random N, sex ratio, MAF mix incl. 1e-6 and K = 1 / 3, override density,
+    pass size, level, row base) -- every case must decompress to the oracle's rows."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "fuzz_parity.py"), "16", "20261018"], capture_output=True,
+                       text=True, cwd=root, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
