@@ -136,18 +136,16 @@ struct dnaf_ctx {
     PinnedBuf h_blocks;
     std::vector<BlockDesc> plan;
 
-    cudaEvent_t ev[8] = {};
     cudaStream_t side = nullptr;           // k_fused_text runs here, concurrently with k_auto
     cudaStream_t side2 = nullptr;          // k_x runs here
     cudaEvent_t ev_join2 = nullptr;
     cudaStream_t copy = nullptr;           // D2H of pass i overlaps the kernels of pass i+1
-    cudaStream_t tot = nullptr;            // 16-byte totals read-backs (never queued behind a data copy)
     struct OutBuf {                        // what must outlive a pass while the next one runs
         DevBuf d_out, d_totals;
         PinnedBuf h_totals, h_out, h_stage;  // h_stage: descriptor uploads of the pass (truly asynchronous H2D)
         size_t stage_used = 0;
         cudaEvent_t ev[6] = {};
-        cudaEvent_t ev_totals = nullptr, ev_copied = nullptr;
+        cudaEvent_t ev_copied = nullptr;
         uint32_t nb = 0;
         uint64_t rows = 0, text = 0;
         bool gen = false, fused = false, generic_blocks = false;
@@ -920,8 +918,6 @@ int close_pass(dnaf_ctx* c, dnaf_ctx::OutBuf& B, uint32_t nb, dnaf_stats* st) {
     return DNAF_OK;
 }
 
-int queue_totals(dnaf_ctx*, dnaf_ctx::OutBuf&) { return DNAF_OK; }   // k_scan_compact stores the totals to host memory itself
-
 // A closed pass: wait for its kernels and totals, account it, and START moving its bytes to the host (straight
 // into a page-locked caller buffer when there is one).  finish_copy() completes the move.
 int start_copy(dnaf_ctx* c, dnaf_ctx::OutBuf& B, Sink& sink, dnaf_stats* st) {
@@ -1231,8 +1227,6 @@ int generate_impl(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t se
                     std::chrono::duration<double, std::micro>(t_l - t_plan1).count());
             trace("launched pass", npass);
         }
-        rc = queue_totals(c, B);
-        if (rc) return rc;
         if (npass >= 1) {
             rc = start_copy(c, c->ob[(npass - 1) % 3], sink, &local);
             if (rc) return rc;
@@ -1281,8 +1275,6 @@ int dnaf_create(int device_ordinal, dnaf_ctx** out) {
     if ((e = cudaSetDevice(device_ordinal)) != cudaSuccess) return bail("cudaSetDevice", e);
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     c->own_stream = true;
-    for (auto& ev : c->ev)
-        if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
     {
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
@@ -1297,11 +1289,9 @@ int dnaf_create(int device_ordinal, dnaf_ctx** out) {
     }
     for (auto& sbf : c->sbuf)
         if ((e = cudaEventCreateWithFlags(&sbf.ev_free, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
-    if ((e = cudaStreamCreateWithFlags(&c->tot, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     for (auto& b : c->ob) {
         for (auto& ev : b.ev)
             if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
-        if ((e = cudaEventCreateWithFlags(&b.ev_totals, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
         if ((e = cudaEventCreateWithFlags(&b.ev_copied, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     }
     if ((e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
@@ -1331,8 +1321,6 @@ void dnaf_destroy(dnaf_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->dev);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    for (auto& ev : c->ev)
-        if (ev) cudaEventDestroy(ev);
     if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
     if (c->side2) { cudaStreamSynchronize(c->side2); cudaStreamDestroy(c->side2); }
     if (c->ev_join2) cudaEventDestroy(c->ev_join2);
@@ -1340,11 +1328,9 @@ void dnaf_destroy(dnaf_ctx* c) {
     if (c->comp) { cudaStreamSynchronize(c->comp); cudaStreamDestroy(c->comp); }
     for (auto& sbf : c->sbuf)
         if (sbf.ev_free) cudaEventDestroy(sbf.ev_free);
-    if (c->tot) { cudaStreamSynchronize(c->tot); cudaStreamDestroy(c->tot); }
     for (auto& b : c->ob) {
         for (auto& ev : b.ev)
             if (ev) cudaEventDestroy(ev);
-        if (b.ev_totals) cudaEventDestroy(b.ev_totals);
         if (b.ev_copied) cudaEventDestroy(b.ev_copied);
     }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
@@ -1773,7 +1759,6 @@ int dnaf_bgzf_compress(dnaf_ctx* c, const uint8_t* text, uint64_t n, int level, 
         if (rc) return rc;
         for (int e = 3; e < 5; ++e) CU(c, cudaEventRecord(B.ev[e], c->stream));   // ev[4]: the compaction stream waits for it
         rc = close_pass(c, B, (uint32_t)c->plan.size(), &local);
-        if (!rc) rc = queue_totals(c, B);
         if (!rc) rc = start_copy(c, B, s, &local);
         if (!rc) rc = finish_copy(c, B, s);
         if (rc) return rc;
