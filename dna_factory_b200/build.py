@@ -14,7 +14,7 @@ LIB_DIR = os.path.join(HERE, "_lib")
 LIB_PATH = os.path.join(LIB_DIR, "libdnaf_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-shared",
-         "-Xcompiler", "-fPIC,-O3,-Wall", "--expt-relaxed-constexpr", "-diag-suppress", "20011,20014,177"]
+         "-Xcompiler", "-fPIC,-O3,-Wall,-pthread", "--expt-relaxed-constexpr", "-diag-suppress", "20011,20014,177"]
 
 
 def sources():

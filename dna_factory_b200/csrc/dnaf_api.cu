@@ -10,12 +10,14 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cerrno>
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/dnaf_b200.h"
@@ -431,6 +433,72 @@ int ensure_tables(dnaf_ctx* c) {
         }
         const int per_block = (int)std::max<size_t>(1, c->h_seg_cell0.size() > 1
                                                            ? (c->h_seg_cell0[1] - c->h_seg_cell0[0] + 63) / 64 : 1);
+        {   // build the tables the caches do not hold yet, on all host threads (about 5 ms each, several hundred
+            // on a first call); the loop below then finds every table cached
+            struct Job { int v; double p; std::pair<uint64_t, uint64_t> key; };
+            std::vector<Job> jobs;
+            std::map<std::pair<int, std::pair<uint64_t, uint64_t>>, int> seen;
+            for (int b = 0; b < nb; ++b) {
+                const double p = c->bucket_p[b];
+                uint64_t pbits;
+                memcpy(&pbits, &p, 8);
+                for (int v = 0; v < kVariants; ++v) {
+                    if (!need[b * kVariants + v]) continue;
+                    const bool with_prefix = (v & 1) == 0;
+                    const uint64_t base = (with_prefix ? c->ph_hash : 0x5bd1e995ull) * 31;
+                    std::pair<uint64_t, uint64_t> key;
+                    bool cached;
+                    int family;
+                    if (v < 2) {
+                        key = {pbits, base + (uint64_t)per_block};
+                        cached = c->atable_cache.count(key) != 0;
+                        family = 0;
+                    } else if (v >= 10) {
+                        key = {pbits, base + (uint64_t)per_block + c->samples_epoch * 0x9E3779B97F4A7C15ull};
+                        cached = c->xtable_cache.count(key) != 0;
+                        family = 1;
+                    } else {
+                        const int cls = (v - 2) / 2;
+                        key = {pbits, base + (uint64_t)(cls + 1) * 1000003ull + c->samples_epoch * 0x9E3779B97F4A7C15ull};
+                        cached = c->table_cache.count(key) != 0;
+                        family = 2 + cls;
+                    }
+                    if (!cached && seen.emplace(std::make_pair(family, key), 1).second) jobs.push_back({v, p, key});
+                }
+            }
+            if (!jobs.empty()) {
+                std::vector<AutoTable> ra(jobs.size());
+                std::vector<XTable> rx;
+                std::vector<FusedTable> rf(jobs.size());
+                bool need_x = false;
+                for (const Job& j : jobs) need_x |= j.v >= 10;
+                if (need_x) rx.resize(jobs.size());
+                std::atomic<size_t> next{0};
+                auto work = [&]() {
+                    for (size_t i = next++; i < jobs.size(); i = next++) {
+                        const Job& j = jobs[i];
+                        const bool with_prefix = (j.v & 1) == 0;
+                        const uint64_t* hist = with_prefix ? c->ph.data() : nullptr;
+                        if (j.v < 2) ra[i] = hosttab::make_auto_table(j.p, hist, per_block, with_prefix);
+                        else if (j.v >= 10) rx[i] = hosttab::make_x_table(j.p, c->h_xspans, per_block, hist);
+                        else rf[i] = hosttab::make_text_table((j.v - 2) / 2, j.p, c->h_sex.data(), c->n, hist);
+                    }
+                };
+                const unsigned nt = std::max(1u, std::min<unsigned>({std::thread::hardware_concurrency(), 16u, (unsigned)jobs.size()}));
+                std::vector<std::thread> pool;
+                for (unsigned t = 1; t < nt; ++t) pool.emplace_back(work);
+                work();
+                for (auto& t : pool) t.join();
+                for (size_t i = 0; i < jobs.size(); ++i) {
+                    const Job& j = jobs[i];
+                    const uint32_t hb = j.v < 2 ? ra[i].hdr_bits : (j.v >= 10 ? rx[i].hdr_bits : rf[i].hdr_bits);
+                    if (hb == 0xFFFFFFFFu) return DNAF_OK;  // header too long: stay on the generic path
+                    if (j.v < 2) c->atable_cache.emplace(j.key, ra[i]);
+                    else if (j.v >= 10) c->xtable_cache.emplace(j.key, rx[i]);
+                    else c->table_cache.emplace(j.key, rf[i]);
+                }
+            }
+        }
         for (int b = 0; b < nb; ++b) {
             const double p = c->bucket_p[b];
             uint64_t pbits;
