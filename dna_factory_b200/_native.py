@@ -21,7 +21,8 @@ class Stats(ctypes.Structure):
     _fields_ = [("rows", ctypes.c_uint64), ("calls", ctypes.c_uint64), ("text_bytes", ctypes.c_uint64),
                 ("bgzf_bytes", ctypes.c_uint64), ("bgzf_blocks", ctypes.c_uint64), ("crc_xor", ctypes.c_uint32),
                 ("kernel_launches", ctypes.c_uint32), ("ms_sample", ctypes.c_float), ("ms_format", ctypes.c_float),
-                ("ms_deflate", ctypes.c_float), ("ms_fused", ctypes.c_float), ("ms_total", ctypes.c_float)]
+                ("ms_deflate", ctypes.c_float), ("ms_fused", ctypes.c_float), ("ms_total", ctypes.c_float),
+                ("ms_auto", ctypes.c_float), ("auto_launches", ctypes.c_uint32), ("auto_text_bytes", ctypes.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -147,6 +147,8 @@ struct dnaf_ctx {
         PinnedBuf h_totals, h_out, h_stage;  // h_stage: descriptor uploads of the pass (truly asynchronous H2D)
         size_t stage_used = 0;
         cudaEvent_t ev[6] = {};
+        cudaEvent_t ev_auto[2] = {};         // around the k_auto launch
+        uint64_t auto_text = 0;              // text bytes of the pass's k_auto blocks (0: no k_auto launch)
         cudaEvent_t ev_copied = nullptr;
         uint32_t nb = 0;
         uint64_t rows = 0, text = 0;
@@ -1011,6 +1013,13 @@ int start_copy(dnaf_ctx* c, dnaf_ctx::OutBuf& B, Sink& sink, dnaf_stats* st) {
         st->ms_deflate += (B.generic_blocks ? t23 : 0.f) + t45;
         if (B.fused) st->ms_fused += t34;
         st->ms_total += t05;
+        if (B.auto_text) {
+            float ta = 0;
+            cudaEventElapsedTime(&ta, B.ev_auto[0], B.ev_auto[1]);
+            st->ms_auto += ta;
+            st->auto_launches += 1;
+            st->auto_text_bytes += B.auto_text;
+        }
         st->rows += B.rows;
         st->text_bytes += B.text;
     }
@@ -1273,14 +1282,24 @@ int generate_impl(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t se
             fa.slot_stride = c->slot_stride;
             fa.sizes = c->sbuf[c->sb].sizes.as<uint32_t>();
             fa.crcs = c->sbuf[c->sb].crcs.as<uint32_t>();
+            CU(c, cudaEventRecord(B.ev_auto[0], c->stream));
             k_auto<<<c->implicit_pass ? c->pass_blocks : (uint32_t)c->fplan.size(), c->fused_threads, auto_smem_bytes(c->fused_threads),
                      c->stream>>>(fa);
+            CU(c, cudaEventRecord(B.ev_auto[1], c->stream));
+            if (c->implicit_pass) {
+                B.auto_text = c->pass_text;
+            } else {   // text of the planned k_auto blocks: prefix on a row's first block, cells, '\n' for '\t' at the row's end
+                uint64_t t = 0;
+                for (const FusedDesc& d : c->fplan) t += 4ull * d.ncells + ((d.flags & 1u) ? c->h_plen[d.row] : 0u);
+                B.auto_text = t;
+            }
             local.kernel_launches += 1;
             CU(c, cudaGetLastError());
         }
         if (!c->tplan.empty()) CU(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
         if (!c->xplan.empty()) CU(c, cudaStreamWaitEvent(c->stream, c->ev_join2, 0));
         CU(c, cudaEventRecord(B.ev[4], c->stream));
+        if (c->fplan.empty() && !c->implicit_pass) B.auto_text = 0;
         B.rows = r1 - r0;
         B.text = c->h_row_off[r1] - c->h_row_off[r0];
         B.gen = grows != 0;
@@ -1360,6 +1379,8 @@ int dnaf_create(int device_ordinal, dnaf_ctx** out) {
     for (auto& b : c->ob) {
         for (auto& ev : b.ev)
             if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
+        for (auto& ev : b.ev_auto)
+            if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
         if ((e = cudaEventCreateWithFlags(&b.ev_copied, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     }
     if ((e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
@@ -1398,6 +1419,8 @@ void dnaf_destroy(dnaf_ctx* c) {
         if (sbf.ev_free) cudaEventDestroy(sbf.ev_free);
     for (auto& b : c->ob) {
         for (auto& ev : b.ev)
+            if (ev) cudaEventDestroy(ev);
+        for (auto& ev : b.ev_auto)
             if (ev) cudaEventDestroy(ev);
         if (b.ev_copied) cudaEventDestroy(b.ev_copied);
     }
@@ -1823,6 +1846,7 @@ int dnaf_bgzf_compress(dnaf_ctx* c, const uint8_t* text, uint64_t n, int level, 
         B.gen = false;
         B.fused = false;
         B.generic_blocks = true;
+        B.auto_text = 0;
         rc = launch_generic(c, &local);
         if (rc) return rc;
         for (int e = 3; e < 5; ++e) CU(c, cudaEventRecord(B.ev[e], c->stream));   // ev[4]: the compaction stream waits for it

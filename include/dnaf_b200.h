@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DNAF_ABI_VERSION 2
+#define DNAF_ABI_VERSION 3
 #define DNAF_KMAX 4 /* alleles per SNP the device path handles (A,C,G,T); K=2 for SnpFactory output */
 
 /* chromosome classes -- the only thing is_haploid() (common/snp.py:102-109) looks at */
@@ -63,6 +63,9 @@ typedef struct dnaf_stats {
     float ms_deflate;          /* ... of the BGZF encoder (+ compaction)                   */
     float ms_fused;            /* ... of the fused sample+format+deflate kernel            */
     float ms_total;            /* first launch to last kernel end, on the library stream   */
+    float ms_auto;             /* ... of the k_auto launches alone (the dominant kernel)    */
+    uint32_t auto_launches;    /* k_auto launches of the call                               */
+    uint64_t auto_text_bytes;  /* uncompressed text bytes those launches emitted            */
 } dnaf_stats;
 
 int dnaf_abi_version(void);
