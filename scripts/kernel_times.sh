@@ -4,7 +4,7 @@ R=${2:-8192}
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --rows-per-step $R"
 $CMD > gpurun_out/plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum,smsp__thread_inst_executed_per_inst_executed.ratio,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active \
-    --clock-control none -k regex:k_ -s 16 -c 10 --csv --log-file "$1" $CMD > gpurun_out/ncu1.log 2>&1
+    --clock-control none -k regex:k_ -s 24 -c 24 --csv --log-file "$1" $CMD > gpurun_out/ncu1.log 2>&1
 python - "$1" <<PY
 import csv,sys
 rows=[r for r in csv.reader(open(sys.argv[1])) if len(r)>10]
