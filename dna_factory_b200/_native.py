@@ -37,8 +37,9 @@ class DnafError(RuntimeError):
 # every symbol include/dnaf_b200.h declares (tests check the built library exports all of them)
 EXPORTS = ["dnaf_abi_version", "dnaf_last_error", "dnaf_create", "dnaf_destroy", "dnaf_set_stream",
            "dnaf_set_chunk_bytes", "dnaf_set_row_base", "dnaf_set_fused", "dnaf_set_samples", "dnaf_set_snps", "dnaf_set_overrides",
-           "dnaf_plan", "dnaf_generate", "dnaf_generate_stream", "dnaf_generate_fd", "dnaf_generate_device", "dnaf_genotypes",
-           "dnaf_text", "dnaf_bgzf_compress", "dnaf_bgzf_bound", "dnaf_bgzf_eof", "dnaf_select_snps", "dnaf_parse_snps_jsonl", "dnaf_format_prefixes",
+           "dnaf_plan", "dnaf_row_offsets", "dnaf_generate", "dnaf_generate_stream", "dnaf_generate_fd", "dnaf_generate_device", "dnaf_genotypes",
+           "dnaf_text", "dnaf_bgzf_compress", "dnaf_bgzf_bound", "dnaf_bgzf_eof", "dnaf_bgzf_scan", "dnaf_block_log",
+           "dnaf_block_log_get", "dnaf_select_snps", "dnaf_parse_snps_jsonl", "dnaf_format_prefixes",
            "dnaf_format_snps_jsonl"]
 
 _lib = None
@@ -71,6 +72,7 @@ def load():
         "dnaf_set_snps": (i32, [vp, u64, u8p, u8p, u32p, u8p, u64p]),
         "dnaf_set_overrides": (i32, [vp, u64, u64p, u32p]),
         "dnaf_plan": (i32, [vp, u64, u64, u64p, u64p]),
+        "dnaf_row_offsets": (i32, [vp, u64, u64, u64p]),
         "dnaf_generate": (i32, [vp, u64, u64, u64, i32, i32, u8p, u64, sp]),
         "dnaf_generate_stream": (i32, [vp, u64, u64, u64, i32, i32, SINK_FN, vp, sp]),
         "dnaf_generate_fd": (i32, [vp, u64, u64, u64, i32, i32, i32, sp]),
@@ -80,6 +82,9 @@ def load():
         "dnaf_bgzf_compress": (i32, [vp, u8p, u64, i32, u8p, u64, sp]),
         "dnaf_bgzf_bound": (u64, [u64]),
         "dnaf_bgzf_eof": (i32, [u8p]),
+        "dnaf_bgzf_scan": (i32, [u8p, u64, u32p, u32p, u64, u64p]),
+        "dnaf_block_log": (i32, [vp, i32]),
+        "dnaf_block_log_get": (i32, [vp, ctypes.POINTER(u32p), ctypes.POINTER(u32p), u64p]),
         "dnaf_parse_snps_jsonl": (ctypes.c_int64, [ctypes.c_char_p, u64, u64, ctypes.POINTER(ctypes.c_int64),
                                                    ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int64), u8p, u8p, f64p,
                                                    ctypes.c_char_p, ctypes.c_uint32, u32p]),
@@ -243,6 +248,26 @@ class Engine:
         self._check(self._lib.dnaf_generate_fd(self._h, row_begin, row_end, seed, rng_mode, level, fd, ctypes.byref(st)))
         return st.as_dict()
 
+    def row_offsets(self, row_begin, row_end):
+        """uint64[row_end-row_begin+1]: text offset of every row of the range (and of its end) from the range's start."""
+        out = np.empty(row_end - row_begin + 1, np.uint64)
+        self._check(self._lib.dnaf_row_offsets(self._h, row_begin, row_end,
+                                               out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))))
+        return out
+
+    def block_log(self, enable=True):
+        """Start (and clear) or stop the record of BGZF blocks later generate* calls hand to the host."""
+        self._check(self._lib.dnaf_block_log(self._h, 1 if enable else 0))
+
+    def block_log_get(self):
+        """(csize, usize) uint32 arrays: compressed and text size of every block logged so far, in order."""
+        cs, us = ctypes.POINTER(ctypes.c_uint32)(), ctypes.POINTER(ctypes.c_uint32)()
+        n = ctypes.c_uint64()
+        self._check(self._lib.dnaf_block_log_get(self._h, ctypes.byref(cs), ctypes.byref(us), ctypes.byref(n)))
+        if not n.value:
+            return np.zeros(0, np.uint32), np.zeros(0, np.uint32)
+        return np.ctypeslib.as_array(cs, (n.value,)).copy(), np.ctypeslib.as_array(us, (n.value,)).copy()
+
     def generate_device(self, row_begin, row_end, seed, level=6, rng_mode=0):
         st = Stats()
         self._check(self._lib.dnaf_generate_device(self._h, row_begin, row_end, seed, rng_mode, level,
@@ -271,6 +296,23 @@ class Engine:
         st = Stats()
         self._check(self._lib.dnaf_bgzf_compress(self._h, _u8(buf), n, level, _u8(out), bound, ctypes.byref(st)))
         return out[:st.bgzf_bytes].tobytes(), st.as_dict()
+
+
+def bgzf_scan(data):
+    """(csize, usize) of every block of a BGZF stream held in memory (host only, no GPU work)."""
+    lib = load()
+    buf = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
+    n = ctypes.c_uint64()
+    rc = lib.dnaf_bgzf_scan(_u8(buf) if len(buf) else None, len(buf), None, None, 0, ctypes.byref(n))
+    if rc:
+        raise DnafError(rc, "not a whole number of BGZF blocks")
+    cs, us = np.empty(n.value, np.uint32), np.empty(n.value, np.uint32)
+    if n.value:
+        u32p = ctypes.POINTER(ctypes.c_uint32)
+        rc = lib.dnaf_bgzf_scan(_u8(buf), len(buf), cs.ctypes.data_as(u32p), us.ctypes.data_as(u32p), n.value, ctypes.byref(n))
+        if rc:
+            raise DnafError(rc, "not a whole number of BGZF blocks")
+    return cs, us
 
 
 def parse_snps_jsonl(data):

@@ -155,7 +155,11 @@ struct dnaf_ctx {
         bool gen = false, fused = false, generic_blocks = false;
         int copy_mode = 0;                   // 0 nothing in flight, 1 DMA into the caller's pinned buffer, 2 via h_out
         uint64_t copy_bytes = 0;
+        const uint8_t* copy_dst = nullptr;   // mode 1: where in the caller's buffer the pass lands
     } ob[3];
+    // optional record of every BGZF block handed to a host sink by dnaf_generate* (dnaf_block_log)
+    bool log_blocks = false;
+    std::vector<uint32_t> log_csize, log_usize;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool attr_done = false;
 
@@ -878,7 +882,35 @@ struct Sink {
     bool device_only = false;
     bool pinned = false;     // buf is page-locked host memory
     int fd = -1;             // file descriptor mode: write() straight from the page-locked staging buffer
+    bool log = false;        // append the blocks to the context's block log as they reach the host
 };
+
+// Walks whole BGZF blocks in [data, data+n): compressed size from BSIZE (the BC subfield), text size from ISIZE.
+// Returns the number of bytes covered by well-formed blocks (== n for a clean stream).
+template <class F>
+uint64_t walk_bgzf(const uint8_t* data, uint64_t n, F&& on_block) {
+    uint64_t o = 0;
+    while (o + 28 <= n) {
+        const uint8_t* h = data + o;
+        if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4) || h[12] != 'B' || h[13] != 'C') break;
+        const uint32_t csize = (uint32_t)(h[16] | (h[17] << 8)) + 1u;
+        if (csize < 26 || o + csize > n) break;
+        const uint8_t* t = h + csize - 4;
+        const uint32_t usize = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
+        on_block(csize, usize);
+        o += csize;
+    }
+    return o;
+}
+
+int append_block_log(dnaf_ctx* c, const uint8_t* data, uint64_t n) {
+    const uint64_t covered = walk_bgzf(data, n, [&](uint32_t cs, uint32_t us) {
+        c->log_csize.push_back(cs);
+        c->log_usize.push_back(us);
+    });
+    if (covered != n) return fail(c, DNAF_E_CUDA, "block log: pass output is not a whole number of BGZF blocks");
+    return DNAF_OK;
+}
 
 int deliver(dnaf_ctx* c, Sink& s, const uint8_t* data, uint64_t n) {
     if (s.fd >= 0) {
@@ -1034,6 +1066,7 @@ int start_copy(dnaf_ctx* c, dnaf_ctx::OutBuf& B, Sink& sink, dnaf_stats* st) {
             return fail(c, DNAF_E_SPACE, "output buffer too small: need more than %llu bytes", (unsigned long long)sink.cap);
         CU(c, cudaMemcpyAsync(sink.buf + sink.used, B.d_out.p, bytes, cudaMemcpyDeviceToHost, c->copy));
         CU(c, cudaEventRecord(B.ev_copied, c->copy));
+        B.copy_dst = sink.buf + sink.used;
         sink.used += bytes;
         B.copy_mode = 1;
         return DNAF_OK;
@@ -1052,6 +1085,10 @@ int finish_copy(dnaf_ctx* c, dnaf_ctx::OutBuf& B, Sink& sink) {
     trace("finish_copy: wait", (int)B.nb);
     CU(c, cudaEventSynchronize(B.ev_copied));
     trace("finish_copy: done", (int)B.nb);
+    if (sink.log) {
+        const int rc = append_block_log(c, mode == 2 ? B.h_out.as<uint8_t>() : B.copy_dst, B.copy_bytes);
+        if (rc) return rc;
+    }
     if (mode == 2) return deliver(c, sink, B.h_out.as<uint8_t>(), B.copy_bytes);
     return DNAF_OK;
 }
@@ -1132,6 +1169,7 @@ int generate_impl(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t se
     CU(c, cudaSetDevice(c->dev));
     dnaf_stats local;
     memset(&local, 0, sizeof local);
+    sink.log = c->log_blocks && !sink.device_only;
     if (sink.buf) {
         cudaPointerAttributes attr;
         if (cudaPointerGetAttributes(&attr, sink.buf) == cudaSuccess) sink.pinned = attr.type == cudaMemoryTypeHost;
@@ -1694,6 +1732,39 @@ uint64_t dnaf_bgzf_bound(uint64_t text_bytes) {
     return text_bytes + blocks * 64 + 1024;
 }
 
+int dnaf_block_log(dnaf_ctx* c, int enable) {
+    if (!c) return DNAF_E_ARG;
+    c->log_blocks = enable != 0;
+    c->log_csize.clear();
+    c->log_usize.clear();
+    return DNAF_OK;
+}
+
+int dnaf_block_log_get(dnaf_ctx* c, const uint32_t** csize, const uint32_t** usize, uint64_t* n_blocks) {
+    if (!c) return DNAF_E_ARG;
+    if (!csize || !usize || !n_blocks) return fail(c, DNAF_E_ARG, "NULL output pointer");
+    *csize = c->log_csize.data();
+    *usize = c->log_usize.data();
+    *n_blocks = c->log_csize.size();
+    return DNAF_OK;
+}
+
+int dnaf_bgzf_scan(const uint8_t* data, uint64_t n_bytes, uint32_t* csize, uint32_t* usize, uint64_t cap,
+                   uint64_t* n_blocks) {
+    if (!n_blocks || (n_bytes && !data)) return DNAF_E_ARG;
+    uint64_t k = 0;
+    const uint64_t covered = walk_bgzf(data, n_bytes, [&](uint32_t cs, uint32_t us) {
+        if (k < cap) {
+            if (csize) csize[k] = cs;
+            if (usize) usize[k] = us;
+        }
+        ++k;
+    });
+    *n_blocks = k;
+    if (covered != n_bytes) return DNAF_E_INPUT;
+    return k > cap && (csize || usize) ? DNAF_E_SPACE : DNAF_OK;
+}
+
 int dnaf_bgzf_eof(uint8_t* out28) {
     static const uint8_t eof[28] = {0x1f, 0x8b, 0x08, 0x04, 0, 0, 0, 0, 0, 0xff, 0x06, 0x00, 0x42, 0x43,
                                     0x02, 0x00, 0x1b, 0x00, 0x03, 0,    0, 0,    0,    0,    0,    0,    0, 0};
@@ -1710,6 +1781,17 @@ int dnaf_plan(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t* text_
     const uint64_t t = c->h_row_off[row_end] - c->h_row_off[row_begin];
     if (text_bytes) *text_bytes = t;
     if (bgzf_bound) *bgzf_bound = dnaf_bgzf_bound(t) + (row_end - row_begin) * 64;
+    return DNAF_OK;
+}
+
+int dnaf_row_offsets(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t* out) {
+    if (!c) return DNAF_E_ARG;
+    int rc = ensure_layout(c);
+    if (rc) return rc;
+    if (row_begin > row_end || row_end > c->S) return fail(c, DNAF_E_ARG, "row range out of bounds");
+    if (!out) return fail(c, DNAF_E_ARG, "out is NULL");
+    const uint64_t base = c->h_row_off[row_begin];
+    for (uint64_t r = row_begin; r <= row_end; ++r) out[r - row_begin] = c->h_row_off[r] - base;
     return DNAF_OK;
 }
 

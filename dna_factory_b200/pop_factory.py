@@ -27,6 +27,7 @@ from datetime import datetime
 import numpy
 
 from . import _native, host
+from .tabix import TabixBuilder
 from .snp import (CHROMOSOME_LIST, CHROMOSOME_MAX_POSITION, CHROMOSOME_PROB, SNPTuples, SnpFactory, SnpTable,  # noqa: F401
                   is_haploid, split_list, stripe_list)
 
@@ -70,11 +71,12 @@ class BgzfSink:
     """Stand-in for the Bio.bgzf.BgzfWriter the reference opens at pop_factory.py:403: text handed to
     write() is buffered and BGZF-encoded on the GPU; write_blocks() appends ready-made BGZF blocks."""
 
-    def __init__(self, filename, engine, compresslevel=6):
+    def __init__(self, filename, engine, compresslevel=6, index=False):
         self._handle = open(filename, "wb")
         self._engine = engine
         self._pending = []
         self.compresslevel = compresslevel
+        self.index = TabixBuilder() if index else None   # block + row table of everything appended (--tbi)
 
     def write(self, data):
         self._pending.append(data.encode("latin-1") if isinstance(data, str) else bytes(data))
@@ -84,11 +86,15 @@ class BgzfSink:
             blob, _ = self._engine.bgzf_compress(b"".join(self._pending), level=self.compresslevel)
             self._pending = []
             self._handle.write(blob)
+            if self.index is not None:
+                self.index.add_blocks(*_native.bgzf_scan(blob))
         self._handle.flush()
 
     def write_blocks(self, blob):
         self.flush()
         self._handle.write(blob)
+        if self.index is not None:
+            self.index.add_blocks(*_native.bgzf_scan(blob))
 
     def close(self):
         self.flush()
@@ -172,7 +178,7 @@ class DeleteriousGroup:
 class PopulationFactory:
     def __init__(self, num_processes=1, generate_snps=False, male_odds=0.5, deleterious_config=None,
                  deleterious_list_path=None, sample_id_offset=0, snps_path=None, output_path=None, seed=None,
-                 gpus=1, gpu_select=False):
+                 gpus=1, gpu_select=False, tbi=False):
         self.deleterious = {}
         self.ordered_snps = []
         self.snp_table = None
@@ -191,6 +197,7 @@ class PopulationFactory:
         self.seed = seed
         self.gpus = max(1, gpus or 1)
         self.gpu_select = bool(gpu_select)
+        self.tbi = bool(tbi)
         self.stats = []
 
     # ------------------------------------------------------------------------------------------ orchestration
@@ -294,7 +301,7 @@ class PopulationFactory:
         self._level = compression_level
         engine = _native.Engine(0)
         try:
-            with BgzfSink(main_file, engine, compresslevel=compression_level) as f:
+            with BgzfSink(main_file, engine, compresslevel=compression_level, index=self.tbi) as f:
                 f.write(gen_vcf_header(fam_data))
                 print("Outputing VCF lines", flush=True)
                 snps = self.snp_table if self.snp_table is not None else self.ordered_snps
@@ -302,6 +309,11 @@ class PopulationFactory:
                 # the GPU path streams, so one call covers the whole list
                 self.write_vcf_snps(fam_data, snps, f, engine=engine)
                 print("%s Finished work chunk 1 of 1." % datetime.now().strftime("%Y-%m-%d %H:%M"), flush=True)
+            if self.tbi:
+                # what `bcftools index -t` (README.md:98-99) would derive by inflating the file again
+                blob, _ = engine.bgzf_compress(f.index.payload(), level=6)
+                with open(main_file + ".tbi", "wb") as t:
+                    t.write(blob + _native.bgzf_eof())
         finally:
             engine.close()
         print("Finished VCF file output.", flush=True)
@@ -323,6 +335,10 @@ class PopulationFactory:
         else:
             orow, osamp = host.override_pairs(fam_data, snps)
         gpus = min(self.gpus, max(1, n_rows))
+        index = getattr(file, "index", None)
+        if index is not None:
+            table = snps if isinstance(snps, SnpTable) else SnpTable.from_snps(snps)
+            index_rows = (table.chrom_labels, table.chrom_idx, table.position)
         if gpus == 1:
             own = engine is None
             eng = engine or _native.Engine(0)
@@ -331,22 +347,30 @@ class PopulationFactory:
                 eng.set_snps(**arrays)
                 eng.set_overrides(orow, osamp)
                 file.flush()
+                if index is not None:
+                    index.add_rows(*index_rows, eng.row_offsets(0, n_rows))
+                    eng.block_log(True)
                 st = eng.generate_fd(0, n_rows, seed, file._handle.fileno(), level=level)   # the handle was just flushed
                 self.stats.append(st)
+                if index is not None:
+                    index.add_blocks(*eng.block_log_get())
+                    eng.block_log(False)
             finally:
                 if own:
                     eng.close()
         else:
-            self._write_multi_gpu(sex, ctl, arrays, orow, osamp, n_rows, seed, level, file, gpus)
+            self._write_multi_gpu(sex, ctl, arrays, orow, osamp, n_rows, seed, level, file, gpus,
+                                  index_rows if index is not None else None)
         print("Finished write_vcf_snps chunk Elapsed time: {:0.4f} seconds".format(time.time() - t0))
 
-    def _write_multi_gpu(self, sex, ctl, arrays, orow, osamp, n_rows, seed, level, file, gpus):
+    def _write_multi_gpu(self, sex, ctl, arrays, orow, osamp, n_rows, seed, level, file, gpus, index_rows=None):
         """Contiguous SNP ranges per GPU, no collective: BGZF blocks concatenate, so every rank's stream is
         spooled and appended in rank order."""
         import tempfile
         bounds = [n_rows * g // gpus for g in range(gpus + 1)]
         spools = [tempfile.TemporaryFile(dir=self.population_dir) for _ in range(gpus)]
         errors = []
+        index, blocks, row_off = getattr(file, "index", None), [None] * gpus, [None]
 
         def run(g):
             try:
@@ -356,7 +380,13 @@ class PopulationFactory:
                     eng.set_overrides(orow, osamp)
                     # rank 0's stream goes straight behind the header; the others spool and are appended in rank order
                     fd = file._handle.fileno() if g == 0 else spools[g].fileno()
+                    if index is not None:
+                        eng.block_log(True)
+                        if g == 0:
+                            row_off[0] = eng.row_offsets(0, n_rows)
                     self.stats.append(eng.generate_fd(bounds[g], bounds[g + 1], seed, fd, level=level))
+                    if index is not None:
+                        blocks[g] = eng.block_log_get()
             except BaseException as e:  # noqa: re-raised on the caller's thread
                 errors.append(e)
 
@@ -378,6 +408,10 @@ class PopulationFactory:
         file._handle.flush()
         for sp in spools:
             sp.close()
+        if index is not None:
+            index.add_rows(*index_rows, row_off[0])
+            for cs, us in blocks:
+                index.add_blocks(cs, us)
 
     # ------------------------------------------------------------------------------------------ deleterious sets
     def load_deleterious(self):
@@ -436,6 +470,8 @@ def parse_cmd_args(args):
     ap.add_argument("--gpus", type=int, default=1, help="GPUs to spread contiguous SNP ranges over (default 1)")
     ap.add_argument("--gpu_select", action="store_true",
                     help="draw and sort the simulated SNPs on the GPU from the --seed stream instead of numpy's global state")
+    ap.add_argument("--tbi", action="store_true",
+                    help="also write population.vcf.gz.tbi (tabix index) from the row and block sizes the writer already knows")
     return ap.parse_args(args)
 
 
@@ -447,7 +483,7 @@ def main(sys_args):
                                 deleterious_list_path=args.deleterious_file, sample_id_offset=args.offset,
                                 male_odds=args.male_odds, deleterious_config=args.deleterious_config,
                                 snps_path=args.snps_file, output_path=args.outdir, seed=args.seed, gpus=args.gpus,
-                                gpu_select=args.gpu_select)
+                                gpu_select=args.gpu_select, tbi=args.tbi)
     factory.generate_population(args.control_size, args.size, args.min_freq, args.max_snps, args.compression_level)
 
 

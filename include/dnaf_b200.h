@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DNAF_ABI_VERSION 3
+#define DNAF_ABI_VERSION 4
 #define DNAF_KMAX 4 /* alleles per SNP the device path handles (A,C,G,T); K=2 for SnpFactory output */
 
 /* chromosome classes -- the only thing is_haploid() (common/snp.py:102-109) looks at */
@@ -154,6 +154,9 @@ uint64_t dnaf_format_snps_jsonl(uint64_t n, const int32_t* chrom_idx, const char
 
 /* Sizes of rows [row_begin,row_end): exact text bytes and an upper bound on the BGZF bytes. */
 int dnaf_plan(dnaf_ctx* ctx, uint64_t row_begin, uint64_t row_end, uint64_t* text_bytes, uint64_t* bgzf_bound);
+/* out[i] = text offset of row row_begin+i relative to row row_begin, i = 0 .. row_end-row_begin (one past the
+ * last row included): the row lengths queue_vcf_snps would produce (pop_factory.py:503-508), for indexing. */
+int dnaf_row_offsets(dnaf_ctx* ctx, uint64_t row_begin, uint64_t row_end, uint64_t* out);
 
 /*
  * The hot path: rows [row_begin,row_end) -> genotype draws -> VCF text -> BGZF blocks.
@@ -186,6 +189,19 @@ int dnaf_text(dnaf_ctx* ctx, uint64_t row_begin, uint64_t row_end, uint64_t seed
 int dnaf_bgzf_compress(dnaf_ctx* ctx, const uint8_t* text, uint64_t n_bytes, int level, uint8_t* out,
                        uint64_t out_cap, dnaf_stats* stats);
 uint64_t dnaf_bgzf_bound(uint64_t text_bytes);
+/* Block table of a BGZF stream held in host memory (no GPU work, no context): compressed and text size of
+ * every block, in order.  With csize == usize == NULL only counts.  DNAF_E_INPUT when the bytes are not a
+ * whole number of well-formed BGZF blocks, DNAF_E_SPACE when there are more than `cap` (n_blocks is still set).
+ * This is what a tabix index needs besides the row sizes: virtual offset = block start << 16 | offset in block
+ * (the reference leaves indexing to `bcftools index`, README.md:98-99). */
+int dnaf_bgzf_scan(const uint8_t* data, uint64_t n_bytes, uint32_t* csize, uint32_t* usize, uint64_t cap,
+                   uint64_t* n_blocks);
+/* The same table for streams that never reach the caller (dnaf_generate_fd) or reach it piecewise:
+ * dnaf_block_log(ctx, 1) clears the log and makes every later dnaf_generate / _stream / _fd call append the
+ * blocks it hands to the host; dnaf_block_log(ctx, 0) stops and clears.  The pointers returned by
+ * dnaf_block_log_get stay valid until the next dnaf_generate* / dnaf_block_log call on the context. */
+int dnaf_block_log(dnaf_ctx* ctx, int enable);
+int dnaf_block_log_get(dnaf_ctx* ctx, const uint32_t** csize, const uint32_t** usize, uint64_t* n_blocks);
 /* The 28-byte BGZF end-of-file block BgzfWriter.close() appends. */
 int dnaf_bgzf_eof(uint8_t* out28);
 
