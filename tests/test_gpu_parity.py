@@ -329,7 +329,7 @@ def test_full_size_c2_properties(native):
 
 
 def test_randomised_shapes_soak():
-    """A short run of scripts/fuzz_parity.py (random N, sex ratio, MAF mix incl. 1e-6 and K = 1 / 3, override density,
+    """A short run of tests/tools/fuzz_parity.py (random N, sex ratio, MAF mix incl. 1e-6 and K = 1 / 3, override density,
     pass size, level, row base) -- every case must decompress to the oracle's rows."""
     import subprocess
     import sys

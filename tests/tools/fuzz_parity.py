@@ -1,7 +1,7 @@
 """Randomised parity soak: populations of random size / sex ratio / MAF mix / override density / pass size through the
-CUDA path (C ABI) against the CPU oracle.  Usage: python scripts/fuzz_parity.py [cases] [seed]"""
+CUDA path (C ABI) against the CPU oracle.  Usage: python tests/tools/fuzz_parity.py [cases] [seed]"""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from types import SimpleNamespace
 from dna_factory_b200 import _native, host

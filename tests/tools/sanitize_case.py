@@ -1,6 +1,6 @@
 """Small multi-kernel case for compute-sanitizer: autosome + X + Y rows, overrides, SNP selection, fd sink."""
 import os, sys, tempfile
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from dna_factory_b200 import _native, host, snp
 from oracle import oracle
