@@ -37,7 +37,7 @@ MALE_ODDS = 0.5
 ROWS_PER_STEP = 32768
 PHILOX_SEED = 0x5EED000000000001
 HOST_SEED = 20260101
-E2E_CHUNK = 1024 << 20   # the library default: passes ramp 1/8, 1/4, 1/2 of it at the start of a call, then whole chunks
+E2E_CHUNK = 1024 << 20   # the library default: passes ramp 1/4, 1/2 of it at the start of a call (1/2 for device-only calls), then whole chunks
 WORKLOAD = ("C2 pop_factory -s 10000 -c 10000 -x 5000000 -f 0.01 -z 2: one step = %d consecutive SNP rows "
             "x 20000 samples (sample -> VCF GT text -> BGZF)" % ROWS_PER_STEP)
 

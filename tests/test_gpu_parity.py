@@ -334,6 +334,6 @@ def test_randomised_shapes_soak():
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "fuzz_parity.py"), "16", "20261018"], capture_output=True,
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "tools", "fuzz_parity.py"), "16", "20261018"], capture_output=True,
                        text=True, cwd=root, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
