@@ -1158,8 +1158,28 @@ uint64_t next_chunk_end(const dnaf_ctx* c, uint64_t r0, uint64_t row_end, uint64
     return std::min(r1, row_end);
 }
 
+int generate_passes(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t seed, int rng_mode, int level,
+                    Sink& sink, dnaf_stats* st);
+
+// The pass pipeline keeps up to three passes in flight.  When a call fails half way (sink error, caller's buffer
+// too small, CUDA error) nothing of it may still be running when the error is returned: a copy could be landing in a
+// caller buffer that is about to be freed, and the next call must find an idle pipeline.
 int generate_impl(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t seed, int rng_mode, int level,
                   Sink& sink, dnaf_stats* st) {
+    const int rc = generate_passes(c, row_begin, row_end, seed, rng_mode, level, sink, st);
+    if (rc && c) {
+        cudaSetDevice(c->dev);
+        cudaStreamSynchronize(c->stream);   // may be the caller's stream (dnaf_set_stream), NULL = the default stream
+        for (cudaStream_t s : {c->side, c->side2, c->comp, c->copy})
+            if (s) cudaStreamSynchronize(s);
+        cudaGetLastError();
+        for (auto& b : c->ob) b.copy_mode = 0;
+    }
+    return rc;
+}
+
+int generate_passes(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t seed, int rng_mode, int level,
+                    Sink& sink, dnaf_stats* st) {
     if (!c) return DNAF_E_ARG;
     if (rng_mode != 0 && rng_mode != 1) return fail(c, DNAF_E_ARG, "rng_mode must be 0 (replay) or 1 (native)");
     if (level < 1 || level > 9) return fail(c, DNAF_E_ARG, "level must be 1..9");

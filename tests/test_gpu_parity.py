@@ -337,3 +337,33 @@ def test_randomised_shapes_soak():
     r = subprocess.run([sys.executable, os.path.join(root, "tests", "tools", "fuzz_parity.py"), "16", "20261018"], capture_output=True,
                        text=True, cwd=root, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_failed_calls_leave_a_usable_context(native):
+    """A call that fails half way (sink raises on its second piece; caller's buffer too small) drains the pass pipeline
+    before it returns, and the same context then produces the same stream as an untouched one."""
+    import ctypes
+    _native, _ = native
+    case = synth_case(3000, 96, seed=21)
+    eng = _engine(native, case, chunk=256 << 10)        # 12 KB rows: many short passes in flight
+    want, _ = eng.generate(0, 96, case.seed, level=2)
+    pieces = []
+
+    def write(b):
+        if len(pieces) == 1:
+            raise OSError("disk full")
+        pieces.append(b)
+
+    with pytest.raises(OSError, match="disk full"):
+        eng.generate_stream(0, 96, case.seed, write, level=2)
+    assert len(pieces) == 1 and want.startswith(pieces[0])
+    got = []
+    eng.generate_stream(0, 96, case.seed, got.append, level=2)
+    assert b"".join(got) == want
+    small = np.empty(len(want) // 2, np.uint8)
+    st = _native.Stats()
+    rc = eng._lib.dnaf_generate(eng._h, 0, 96, case.seed, 0, 2, small.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)),
+                                small.nbytes, ctypes.byref(st))
+    assert rc == -4 and b"too small" in eng._lib.dnaf_last_error(eng._h)
+    again, _ = eng.generate(0, 96, case.seed, level=2)
+    assert again == want
