@@ -375,14 +375,13 @@ __global__ void __maxnreg__(56) k_auto(const AutoArgs a) {
         const uint64_t prow = a.row_base + d.row;
         const uint32_t r_lo = (uint32_t)prow, r_hi = (uint32_t)(prow >> 32);
         const uint32_t g0 = cs >> 4;
-        uint32_t eq[4], lt[4], valid[4];
+        uint32_t eq[4], lt[4];
+        const int slots0 = (int)(2u * a.sv.n) - (int)(32u * g0);   // allele slots from this span's first group to the row's end
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
-            const uint32_t g = g0 + w;
-            const uint32_t slots = 32u * g < 2u * a.sv.n ? 2u * a.sv.n - 32u * g : 0u;
-            valid[w] = slots >= 32u ? 0xFFFFFFFFu : ((1u << slots) - 1u);
-            eq[w] = valid[w];
-            lt[w] = 0;
+            // lanes beyond the last sample start out decided ("U <= T": reference allele, mask bit 0)
+            eq[w] = __funnelshift_lc(0xFFFFFFFFu, 0u, (uint32_t)max(slots0 - 32 * w, 0));
+            lt[w] = ~eq[w];
         }
         // the first 8 bits of every lane decide 99.6 % of them: two calls per group, no divergence
 #pragma unroll
@@ -407,7 +406,7 @@ __global__ void __maxnreg__(56) k_auto(const AutoArgs a) {
                 if (k == w) { eq[k] = e; lt[k] = l; }
         }
 #pragma unroll
-        for (int w = 0; w < 4; ++w) m[w] = ~(lt[w] | eq[w]) & valid[w];   // U <= T -> reference allele
+        for (int w = 0; w < 4; ++w) m[w] = ~(lt[w] | eq[w]);   // U <= T -> reference allele
     }
     // forced-minor cells (pop_factory.py:495-499)
     if (nc > 0) {
