@@ -124,7 +124,7 @@ def cpu_reference_run(steps, warmup, budget_s=20.0):
     oracle.build()
     # every host thread the box offers, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1)
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    rows = 256
+    rows = 512   # 6 timed steps = 6.1e7 calls: about 1 s of wall clock, ~15 s of CPU time on 16 threads
     sex, ctl, table, orow, osamp = synth_population(rows * (steps + warmup), window=rows)
     snps_all = table.to_snps()
     from types import SimpleNamespace
