@@ -310,6 +310,28 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src));
 }
 
+// 1-D bulk copy global -> shared (cp.async.bulk, the TMA engine): 16-byte aligned both sides, size a multiple of 16;
+// the bytes are counted on the mbarrier at `mbar` (shared-window address)
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(mbar)
+                 : "memory");
+}
+
+// Wait for phase `parity` of an mbarrier (try_wait sleeps in hardware); a copy that never lands traps instead of hanging.
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    for (uint32_t spins = 0;; ++spins) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok)
+                     : "r"(mbar), "r"(parity)
+                     : "memory");
+        if (ok) return;
+        if (spins > (1u << 20)) __trap();
+    }
+}
+
 __global__ void __maxnreg__(56) k_auto(const AutoArgs a) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const uint32_t tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31u, wid = tid >> 5;
@@ -338,24 +360,18 @@ __global__ void __maxnreg__(56) k_auto(const AutoArgs a) {
         d.table = 2u * __ldg(&a.bucket[d.row]) + (sg == 0u ? 0u : 1u);
     }
     const AutoTable* __restrict__ tb = a.tables + d.table;
-    {   // code tables of this block's bucket -> shared memory, asynchronously: they are needed after the draws
-        const uint4* src = reinterpret_cast<const uint4*>(tb->lut);
-        uint4* dst = reinterpret_cast<uint4*>(s_lut);
-#pragma unroll
-        for (uint32_t k = 0; k < 8; ++k) {   // nthr >= 64
-            const uint32_t i = tid + k * nthr;
-            if (i < 512u) cp_async16(dst + i, src + i);
-        }
-        const uint4* src2 = reinterpret_cast<const uint4*>(tb->len_tok);
-        uint4* dst2 = reinterpret_cast<uint4*>(s_len);
-#pragma unroll
-        for (uint32_t k = 0; k < 2; ++k) {
-            const uint32_t i = tid + k * nthr;
-            if (i < kATabWords / 4u) cp_async16(dst2 + i, src2 + i);
-        }
-        asm volatile("cp.async.commit_group;\n" ::);
-        if (tid == 6) { s_misc[16] = 0; s_misc[17] = 0; }
+    // code tables of this block's bucket -> shared memory by two bulk copies (TMA, one thread issues them) that land
+    // under the draws; completion is counted in bytes on an mbarrier every thread waits on before the token pass
+    const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(s_misc + 22);   // 8-byte aligned: nthr is a multiple of 32
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(mbar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(mbar), "r"(8192u + kATabWords * 4u) : "memory");
+        bulk_g2s(s_lut, tb->lut, 8192u, mbar);
+        bulk_g2s(s_len, tb->len_tok, kATabWords * 4u, mbar);
     }
+    if (tid == 6) { s_misc[16] = 0; s_misc[17] = 0; }
     const bool starts_row = d.flags & 1u, ends_row = (d.flags >> 1) & 1u;
     const uint64_t pb = a.nv.pre_off[d.row];
     const uint32_t plen = starts_row ? (uint32_t)(a.nv.pre_off[d.row + 1] - pb) : 0u;
@@ -476,8 +492,8 @@ __global__ void __maxnreg__(56) k_auto(const AutoArgs a) {
         }
     }
     s_last2[tid] = mp[3] >> 30;
-    asm volatile("cp.async.wait_group 0;\n" ::);
-    __syncthreads();
+    __syncthreads();        // also orders the mbarrier's initialisation before the waits
+    mbar_wait(mbar, 0u);    // the code tables have landed
     if (lane == 0 && crc) atomicXor(&s_misc[16], crc);
     const uint32_t carry = tid ? s_last2[tid - 1] : (mp[0] & 3u);
     uint32_t nz = 0;
