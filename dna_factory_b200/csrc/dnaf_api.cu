@@ -1324,6 +1324,7 @@ int generate_passes(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t 
             fa.desc = c->implicit_pass ? nullptr : c->d_fdesc.as<FusedDesc>();
             fa.row0 = r0;
             fa.nseg = (uint32_t)c->h_seg_crc.size();
+            fa.nseg_magic = fa.nseg > 1 ? (uint32_t)(((1ull << 32) + fa.nseg - 1) / fa.nseg) : 0u;
             fa.seginfo = c->d_seginfo.as<uint32_t>();
             fa.bucket = c->d_bucket.as<uint16_t>();
             fa.ovr_first = c->d_ovr_first.as<uint32_t>();

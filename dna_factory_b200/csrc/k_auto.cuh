@@ -51,6 +51,7 @@ struct AutoArgs {
                                // segment b % nseg of row row0 + b / nseg (no host planning, nothing to upload)
     uint64_t row0;
     uint32_t nseg;
+    uint32_t nseg_magic;       // ceil(2^32 / nseg): block / nseg == umulhi(block, magic) while block * nseg < 2^32
     const uint32_t* seginfo;   // [nseg][3]: first cell, cells, template CRC of the segment
     const uint16_t* bucket;    // per row: MAF bucket (tables 2*bucket, 2*bucket + 1)
     const uint32_t* ovr_first; // [rows + 1]: first override of every row
@@ -348,7 +349,7 @@ __global__ void __maxnreg__(56) k_auto(const AutoArgs a) {
     if (a.desc) {
         d = a.desc[blockIdx.x];
     } else {
-        const uint32_t rl = blockIdx.x / a.nseg, sg = blockIdx.x - rl * a.nseg;
+        const uint32_t rl = a.nseg_magic ? __umulhi(blockIdx.x, a.nseg_magic) : blockIdx.x, sg = blockIdx.x - rl * a.nseg;   // magic 0: one segment per row
         d.row = a.row0 + rl;
         d.cell0 = __ldg(&a.seginfo[3u * sg]);
         d.ncells = __ldg(&a.seginfo[3u * sg + 1u]);
