@@ -566,20 +566,35 @@ __global__ void __maxnreg__(56) k_auto(const AutoArgs a) {
         const uint32_t hdr_words = (hdr_bits + 31u) / 32u;
         const uint32_t hw4 = (hdr_words + 3u) & ~3u;   // <= 64 <= nthr
         if (tid < hw4) words[tid] = tid < hdr_words ? s_hdr[tid] : 0u;
-        {
+        const bool overflow = s_misc[17] != 0;   // final: pass 1 ended before the scan's barrier
+        const uint32_t ppos = hdr_bits + pre_off;                 // first bit of this thread's prefix literal
+        const uint32_t dst = hdr_bits + total_pre + span_off;     // first bit of this span in the block
+        if (overflow) {   // the slow pass 2 ORs every word
             uint4* w4 = reinterpret_cast<uint4*>(words + hw4);
             const uint32_t n4 = out_words + 2u > hw4 ? (out_words + 2u - hw4 + 3u) / 4u : 0u;
             for (uint32_t i = tid; i < n4; i += nthr) w4[i] = make_uint4(0u, 0u, 0u, 0u);
+        } else {
+            // Only words that two writers share are OR-ed into -- the words of the prefix literals and the first and last
+            // word of every span; words in between belong to one span and are stored whole.  Zero just those (the words
+            // up to hw4 are initialised by the header store above).
+            if (pre_bits) {
+                const uint32_t wi = ppos >> 5;
+                if (wi >= hw4) words[wi] = 0u;
+                if (wi + 1u >= hw4) words[wi + 1u] = 0u;
+            }
+            if (worker) {
+                const uint32_t first = dst >> 5, last = (dst + my_bits - 1u) >> 5;
+                if (first >= hw4) words[first] = 0u;
+                if (last >= hw4) words[last] = 0u;
+            }
         }
         __syncthreads();
-        const bool overflow = s_misc[17] != 0;
         if (pre_bits) {  // prefix literal: at most 15 bits
-            const uint32_t pos = hdr_bits + pre_off, wi = pos >> 5, sh = pos & 31u, v = pre_tok & 0xFFFFFFu;
+            const uint32_t wi = ppos >> 5, sh = ppos & 31u, v = pre_tok & 0xFFFFFFu;
             atomicOr(&words[wi], v << sh);
             if (sh + pre_bits > 32) atomicOr(&words[wi + 1], v >> (32 - sh));
         }
         if (worker) {
-            const uint32_t dst = hdr_bits + total_pre + span_off;  // first bit of this span in the block
             if (!overflow) {
                 // ---- pass 2 (fast): move the staged bits to their final position; only the first and the last
                 // destination word can be shared with a neighbour
