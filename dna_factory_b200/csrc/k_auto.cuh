@@ -32,7 +32,7 @@ constexpr uint32_t kLutLong = 1u << 17;               // flag of a LUT entry who
 
 // Static code tables of one (MAF bucket, with/without prefix) pair.
 struct AutoTable {
-    // ---- first kATabWords words + the LUT are copied to shared memory by every block (cp.async, 16-byte units)
+    // ---- first kATabWords words + the LUT are copied to shared memory by every block (bulk copies, 16-byte units)
     uint32_t len_tok[264];   // [g] token bridging g predicted bytes: 0 empty, 1 '\t' literal, 3..258 match; [259 + bit]: '/' + allele literal
     uint32_t lit[8];         // cell literals by id: code | bits << 24
     uint32_t eob;
@@ -305,10 +305,6 @@ __device__ __forceinline__ uint32_t mul_tab(const uint32_t* __restrict__ t, uint
 // dynamic shared memory carve-up, nthr = blockDim.x
 __host__ __device__ inline uint32_t auto_smem_bytes(uint32_t nthr) {
     return 8192u + kATabWords * 4u + ((uint32_t)(kAStage + 2) * nthr + nthr + 24u) * 4u + 20u * nthr + 16u;
-}
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src));
 }
 
 // 1-D bulk copy global -> shared (cp.async.bulk, the TMA engine): 16-byte aligned both sides, size a multiple of 16;

@@ -247,17 +247,17 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 4) k_x(const XArgs a) {
 
     const FusedDesc d = a.desc[blockIdx.x];
     const XTable* __restrict__ tb = a.tables + d.table;
-    {
-        const uint4* src2 = reinterpret_cast<const uint4*>(tb->len_tok);
-        uint4* dst2 = reinterpret_cast<uint4*>(s_len);
-#pragma unroll
-        for (uint32_t k = 0; k < 2; ++k) {
-            const uint32_t i = tid + k * nthr;
-            if (i < kATabWords / 4u) cp_async16(dst2 + i, src2 + i);
-        }
-        asm volatile("cp.async.commit_group;\n" ::);
-        if (tid == 6) { s_misc[16] = 0; s_misc[17] = 0; }
+    // match / literal tokens and the block header -> shared memory by one TMA bulk copy (see k_auto); the unit LUT stays in L2
+    static_assert(sizeof(XTable) % 16 == 0, "XTable must be 16-byte aligned for the bulk copy");
+    const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(s_misc + 22);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(mbar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(mbar), "r"(kATabWords * 4u) : "memory");
+        bulk_g2s(s_len, tb->len_tok, kATabWords * 4u, mbar);
     }
+    if (tid == 6) { s_misc[16] = 0; s_misc[17] = 0; }
     const bool starts_row = d.flags & 1u, ends_row = (d.flags >> 1) & 1u;
     const uint64_t pb = a.nv.pre_off[d.row];
     const uint32_t plen = starts_row ? (uint32_t)(a.nv.pre_off[d.row + 1] - pb) : 0u;
@@ -370,8 +370,8 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 4) k_x(const XArgs a) {
         }
     }
     s_last2[tid] = L >= 2 ? ((bit128(c, (int)L - 1) << 1) | bit128(c, (int)L - 2)) : 0u;
-    asm volatile("cp.async.wait_group 0;\n" ::);
-    __syncthreads();
+    __syncthreads();        // also orders the mbarrier's initialisation before the waits
+    mbar_wait(mbar, 0u);
     if (lane == 0 && crc) atomicXor(&s_misc[16], crc);
     const uint32_t carry = tid ? s_last2[tid - 1] : (cpad[0] & 3u);
     const bool worker = nc > 0;
