@@ -433,12 +433,17 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 4) k_x(const XArgs a) {
             }
             prev_end = pos + (int)(e.y >> 28);
         }
-        // the positions after the last whole unit, event by event
+        // the positions after the last whole unit, event by event: they all lie in the 6-position window of unit `nfull`
+        // (bit j + 2 = position 4 * nfull + j, j = -2 .. 3), read like the loop above reads its units
         {
+            const int k0 = 4 * nfull;
+            const uint32_t vt = (uint32_t)cpb[nfull >> 1] | ((uint32_t)cpb[(nfull >> 1) + 1] << 8);
+            const uint32_t c6 = (vt >> (4 * (nfull & 1))) & 63u;
+            const uint32_t s6 = nfull < 32 ? (uint32_t)xs->sk6[nfull] : (xs->sk[3] >> 30);
             auto lit_at = [&](int q) {
-                const int k = q >> 1;
-                if (q & 1) return s_lits[bit128(xs->sk, k) ? kLitSlash : kLitTab];
-                return s_lits[bit128(cpad, k)];
+                const int j = (q >> 1) - k0 + 2;
+                if (q & 1) return s_lits[((s6 >> j) & 1u) ? kLitSlash : kLitTab];
+                return s_lits[(c6 >> j) & 1u];
             };
             auto gap_to = [&](int q) {
                 const int g = q - prev_end;
@@ -452,19 +457,19 @@ __global__ void __launch_bounds__(kFusedMaxThreads, 4) k_x(const XArgs a) {
                     }
                 }
             };
-            for (int k = 4 * nfull; k < (int)L; ++k) {
-                const uint32_t ck2 = k >= 2 ? bit128(cpad, k - 2) : (carry >> k) & 1u;
-                const uint32_t sk2 = k >= 2 ? bit128(xs->sk, k - 2) : (xs->skc >> k) & 1u;
-                if (bit128(cpad, k) != ck2) {
+            for (int k = k0; k < (int)L; ++k) {
+                const int j = k - k0;   // window bit j + 2 = position k, bit j = position k - 2
+                const uint32_t cb = (c6 >> (j + 2)) & 1u, sb = (s6 >> (j + 2)) & 1u;
+                if (cb != ((c6 >> j) & 1u)) {
                     gap_to(2 * k);
-                    const uint32_t tk = s_lits[bit128(cpad, k)];
+                    const uint32_t tk = s_lits[cb];
                     st.put64(tk & 0xFFFFFFu, 0u, tk >> 24);
                     prev_end = 2 * k + 1;
                 }
                 if (p_end && k == (int)L - 1) break;
-                if (bit128(xs->sk, k) != sk2) {
+                if (sb != ((s6 >> j) & 1u)) {
                     gap_to(2 * k + 1);
-                    const uint32_t tk = s_lits[bit128(xs->sk, k) ? kLitSlash : kLitTab];
+                    const uint32_t tk = s_lits[sb ? kLitSlash : kLitTab];
                     st.put64(tk & 0xFFFFFFu, 0u, tk >> 24);
                     prev_end = 2 * k + 2;
                 }
