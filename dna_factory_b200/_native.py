@@ -35,12 +35,13 @@ class DnafError(RuntimeError):
 
 
 # every symbol include/dnaf_b200.h declares (tests check the built library exports all of them)
+ABI_VERSION = 5   # include/dnaf_b200.h DNAF_ABI_VERSION
 EXPORTS = ["dnaf_abi_version", "dnaf_last_error", "dnaf_create", "dnaf_destroy", "dnaf_set_stream",
            "dnaf_set_chunk_bytes", "dnaf_set_row_base", "dnaf_set_fused", "dnaf_set_samples", "dnaf_set_snps", "dnaf_set_overrides",
-           "dnaf_plan", "dnaf_row_offsets", "dnaf_generate", "dnaf_generate_stream", "dnaf_generate_fd", "dnaf_generate_device", "dnaf_genotypes",
+           "dnaf_plan", "dnaf_row_offsets", "dnaf_generate", "dnaf_generate_stream", "dnaf_generate_fd", "dnaf_generate_fd_at", "dnaf_generate_device", "dnaf_genotypes",
            "dnaf_text", "dnaf_bgzf_compress", "dnaf_bgzf_bound", "dnaf_bgzf_eof", "dnaf_bgzf_scan", "dnaf_block_log",
            "dnaf_block_log_get", "dnaf_select_snps", "dnaf_parse_snps_jsonl", "dnaf_format_prefixes",
-           "dnaf_format_snps_jsonl"]
+           "dnaf_format_snps_jsonl", "dnaf_debug_lz_block"]
 
 _lib = None
 
@@ -73,10 +74,11 @@ def load():
         "dnaf_set_overrides": (i32, [vp, u64, u64p, u32p]),
         "dnaf_plan": (i32, [vp, u64, u64, u64p, u64p]),
         "dnaf_row_offsets": (i32, [vp, u64, u64, u64p]),
-        "dnaf_generate": (i32, [vp, u64, u64, u64, i32, i32, u8p, u64, sp]),
-        "dnaf_generate_stream": (i32, [vp, u64, u64, u64, i32, i32, SINK_FN, vp, sp]),
-        "dnaf_generate_fd": (i32, [vp, u64, u64, u64, i32, i32, i32, sp]),
-        "dnaf_generate_device": (i32, [vp, u64, u64, u64, i32, i32, sp]),
+        "dnaf_generate": (i32, [vp, u64, u64, u64, i32, u8p, u64, sp]),
+        "dnaf_generate_stream": (i32, [vp, u64, u64, u64, i32, SINK_FN, vp, sp]),
+        "dnaf_generate_fd": (i32, [vp, u64, u64, u64, i32, i32, sp]),
+        "dnaf_generate_fd_at": (i32, [vp, u64, u64, u64, i32, i32, u64, sp]),
+        "dnaf_generate_device": (i32, [vp, u64, u64, u64, i32, sp]),
         "dnaf_genotypes": (i32, [vp, u64, u64, u64, u8p, u64]),
         "dnaf_text": (i32, [vp, u64, u64, u64, u8p, u64, u64p]),
         "dnaf_bgzf_compress": (i32, [vp, u8p, u64, i32, u8p, u64, sp]),
@@ -92,6 +94,7 @@ def load():
                                        ctypes.POINTER(ctypes.c_int64), u8p, u8p, u8p, u64p]),
         "dnaf_format_snps_jsonl": (u64, [u64, ctypes.POINTER(ctypes.c_int32), ctypes.c_char_p, ctypes.POINTER(ctypes.c_int64),
                                          ctypes.POINTER(ctypes.c_int64), u8p, u8p, u32p, ctypes.c_char_p, u32p, u8p]),
+        "dnaf_debug_lz_block": (ctypes.c_int64, [ctypes.c_double, i32, u32p, ctypes.c_uint32, u8p, ctypes.c_uint32, i32, u8p, u64]),
         "dnaf_select_snps": (i32, [vp, u64, u64, ctypes.c_uint32, f64p, f64p, u8p, ctypes.c_uint32, f64p, i32, u32p, u8p, u8p,
                                    u32p, u8p, u8p]),
     }
@@ -99,6 +102,9 @@ def load():
         fn = getattr(L, name)
         fn.restype = res
         fn.argtypes = args
+    if L.dnaf_abi_version() != ABI_VERSION:
+        raise ImportError("%s has ABI %d, this binding needs %d: rebuild with `python -m dna_factory_b200.build --force`"
+                          % (LIB_PATH, L.dnaf_abi_version(), ABI_VERSION))
     _lib = L
     return L
 
@@ -206,23 +212,23 @@ class Engine:
         return t.value, b.value
 
     # -- the hot path
-    def generate(self, row_begin, row_end, seed, level=6, rng_mode=0):
+    def generate(self, row_begin, row_end, seed, level=6):
         """BGZF bytes (whole blocks, no EOF) of rows [row_begin,row_end) -> (bytes, stats dict)."""
         _, bound = self.plan(row_begin, row_end)
         out = np.empty(bound, dtype=np.uint8)
         st = Stats()
-        self._check(self._lib.dnaf_generate(self._h, row_begin, row_end, seed, rng_mode, level, _u8(out), bound,
+        self._check(self._lib.dnaf_generate(self._h, row_begin, row_end, seed, level, _u8(out), bound,
                                             ctypes.byref(st)))
         return out[:st.bgzf_bytes].tobytes(), st.as_dict()
 
-    def generate_into(self, row_begin, row_end, seed, out, level=6, rng_mode=0):
+    def generate_into(self, row_begin, row_end, seed, out, level=6):
         """Same, into a caller-owned uint8 numpy buffer; returns stats dict."""
         st = Stats()
-        self._check(self._lib.dnaf_generate(self._h, row_begin, row_end, seed, rng_mode, level, _u8(out), out.nbytes,
+        self._check(self._lib.dnaf_generate(self._h, row_begin, row_end, seed, level, _u8(out), out.nbytes,
                                             ctypes.byref(st)))
         return st.as_dict()
 
-    def generate_stream(self, row_begin, row_end, seed, write, level=6, rng_mode=0):
+    def generate_stream(self, row_begin, row_end, seed, write, level=6):
         """Calls write(bytes) for consecutive pieces of the stream; returns stats dict."""
         err = []
 
@@ -235,17 +241,23 @@ class Engine:
                 return 1
 
         st = Stats()
-        rc = self._lib.dnaf_generate_stream(self._h, row_begin, row_end, seed, rng_mode, level, SINK_FN(cb), None,
+        rc = self._lib.dnaf_generate_stream(self._h, row_begin, row_end, seed, level, SINK_FN(cb), None,
                                             ctypes.byref(st))
         if err:
             raise err[0]
         self._check(rc)
         return st.as_dict()
 
-    def generate_fd(self, row_begin, row_end, seed, fd, level=6, rng_mode=0):
+    def generate_fd(self, row_begin, row_end, seed, fd, level=6):
         """Same stream, written to an open file descriptor by the library itself; returns stats dict."""
         st = Stats()
-        self._check(self._lib.dnaf_generate_fd(self._h, row_begin, row_end, seed, rng_mode, level, fd, ctypes.byref(st)))
+        self._check(self._lib.dnaf_generate_fd(self._h, row_begin, row_end, seed, level, fd, ctypes.byref(st)))
+        return st.as_dict()
+
+    def generate_fd_at(self, row_begin, row_end, seed, fd, file_offset, level=6):
+        """Same stream, written with pwrite() at `file_offset` of an open file descriptor; returns stats dict."""
+        st = Stats()
+        self._check(self._lib.dnaf_generate_fd_at(self._h, row_begin, row_end, seed, level, fd, int(file_offset), ctypes.byref(st)))
         return st.as_dict()
 
     def row_offsets(self, row_begin, row_end):
@@ -268,9 +280,9 @@ class Engine:
             return np.zeros(0, np.uint32), np.zeros(0, np.uint32)
         return np.ctypeslib.as_array(cs, (n.value,)).copy(), np.ctypeslib.as_array(us, (n.value,)).copy()
 
-    def generate_device(self, row_begin, row_end, seed, level=6, rng_mode=0):
+    def generate_device(self, row_begin, row_end, seed, level=6):
         st = Stats()
-        self._check(self._lib.dnaf_generate_device(self._h, row_begin, row_end, seed, rng_mode, level,
+        self._check(self._lib.dnaf_generate_device(self._h, row_begin, row_end, seed, level,
                                                    ctypes.byref(st)))
         return st.as_dict()
 
@@ -387,6 +399,20 @@ def format_snps_jsonl(ids, chrom_idx, labels, position, n_alleles, nts, cum):
                                       pos.ctypes.data_as(i64p), ids.ctypes.data_as(i64p), _u8(k), _u8(nt),
                                       ridx.ctypes.data_as(u32p), b"".join(strs), roff.ctypes.data_as(u32p), _u8(out))
     return out[:used].tobytes()
+
+
+def debug_lz_block(p_minor, level, allele_bits, n_cells, prefix=b"", ends_row=False):
+    """Raw deflate bytes of one autosome segment under the LZ tier `level` (host self-test hook, see dnaf_b200.h)."""
+    L = load()
+    bits = np.ascontiguousarray(allele_bits, dtype=np.uint32)
+    assert bits.size * 32 >= 2 * n_cells
+    pre = np.frombuffer(bytes(prefix) + b"\0", dtype=np.uint8)
+    out = np.empty(4 * n_cells + 1024, dtype=np.uint8)
+    n = L.dnaf_debug_lz_block(float(p_minor), int(level), bits.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), int(n_cells),
+                              _u8(pre), len(prefix), 1 if ends_row else 0, _u8(out), out.size)
+    if n < 0:
+        raise DnafError(int(n), "dnaf_debug_lz_block failed")
+    return out[:n].tobytes()
 
 
 def bgzf_eof():

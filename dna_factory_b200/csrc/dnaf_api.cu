@@ -198,6 +198,12 @@ struct dnaf_ctx {
     std::map<std::pair<uint64_t, uint64_t>, XTable> xtable_cache;
     std::vector<uint32_t> h_mspan, h_mpre_x;
     std::map<std::pair<uint64_t, uint64_t>, AutoTable> atable_cache;
+    // k_lz (k_lz.cuh): code tables per (bucket, starts-row) of the LZ tier in use (-z 4..9)
+    DevBuf d_ltables;
+    std::map<std::pair<std::pair<uint64_t, uint64_t>, int>, LzTable> ltable_cache;
+    std::vector<uint64_t> ltables_sig;     // what d_ltables currently holds
+    bool lz_ok = false;
+    bool lz_attr_done = false;
     std::vector<uint32_t> h_mtail, h_mpre;
     DevBuf d_pfx_state;
     PinnedBuf h_present;                   // byte values seen in the row prefixes (written by k_prefix_crc)
@@ -621,6 +627,73 @@ int ensure_tables(dnaf_ctx* c) {
     return DNAF_OK;
 }
 
+// The LZ tiers' code tables (k_lz.cuh) for the level of this call: one per (bucket with autosome rows, starts-row).
+// Built lazily at the first dnaf_generate* call that asks for -z >= 4, cached per (bucket, prefix model, level).
+int ensure_lz_tables(dnaf_ctx* c, int level) {
+    c->lz_ok = false;
+    if (!c->fused_ok || level < 4 || c->h_seg_crc.empty()) return DNAF_OK;
+    const int nb = (int)c->bucket_p.size();
+    const int per_block = (int)std::max<size_t>(1, c->h_seg_cell0.size() > 1
+                                                       ? (c->h_seg_cell0[1] - c->h_seg_cell0[0] + 63) / 64 : 1);
+    std::vector<uint64_t> sig;
+    sig.push_back(c->ph_hash);
+    sig.push_back((uint64_t)level);
+    sig.push_back((uint64_t)per_block);
+    for (int b = 0; b < nb; ++b) {
+        uint64_t pbits;
+        memcpy(&pbits, &c->bucket_p[b], 8);
+        sig.push_back(c->need_sticky[(size_t)b * kVariants] ? pbits : 0);
+    }
+    if (sig == c->ltables_sig) {
+        c->lz_ok = true;
+        return DNAF_OK;
+    }
+    struct Job { int b, v; std::pair<std::pair<uint64_t, uint64_t>, int> key; };
+    std::vector<Job> jobs;
+    std::map<std::pair<std::pair<uint64_t, uint64_t>, int>, int> seen;
+    auto key_of = [&](int b, int v) {
+        uint64_t pbits;
+        memcpy(&pbits, &c->bucket_p[b], 8);
+        return std::make_pair(std::make_pair(pbits, (v == 0 ? c->ph_hash : 0x5bd1e995ull) * 31 + (uint64_t)per_block), level);
+    };
+    for (int b = 0; b < nb; ++b) {
+        if (!c->need_sticky[(size_t)b * kVariants]) continue;
+        for (int v = 0; v < 2; ++v) {
+            auto key = key_of(b, v);
+            if (!c->ltable_cache.count(key) && seen.emplace(key, 1).second) jobs.push_back({b, v, key});
+        }
+    }
+    if (!jobs.empty()) {
+        std::vector<LzTable> res(jobs.size());
+        std::atomic<size_t> next{0};
+        auto work = [&]() {
+            for (size_t i = next++; i < jobs.size(); i = next++)
+                res[i] = hosttab::make_lz_table(c->bucket_p[jobs[i].b], jobs[i].v == 0 ? c->ph.data() : nullptr, per_block,
+                                                jobs[i].v == 0, level);
+        };
+        const unsigned nt = std::max(1u, std::min<unsigned>({std::thread::hardware_concurrency(), 16u, (unsigned)jobs.size()}));
+        std::vector<std::thread> pool;
+        for (unsigned t = 1; t < nt; ++t) pool.emplace_back(work);
+        work();
+        for (auto& t : pool) t.join();
+        for (size_t i = 0; i < jobs.size(); ++i) {
+            if (res[i].hdr_bits == 0xFFFFFFFFu) return DNAF_OK;   // header too long: the call stays on k_auto
+            c->ltable_cache.emplace(jobs[i].key, res[i]);
+        }
+    }
+    std::vector<LzTable> tabs((size_t)nb * 2);
+    memset(tabs.data(), 0, tabs.size() * sizeof(LzTable));
+    for (int b = 0; b < nb; ++b) {
+        if (!c->need_sticky[(size_t)b * kVariants]) continue;
+        for (int v = 0; v < 2; ++v) tabs[(size_t)b * 2 + v] = c->ltable_cache.at(key_of(b, v));
+    }
+    const int rc = upload(c, c->d_ltables, tabs.data(), tabs.size());
+    if (rc) return rc;
+    c->ltables_sig = sig;
+    c->lz_ok = true;
+    return DNAF_OK;
+}
+
 // Segments of an autosome row (balanced, at most 254 spans of 64 samples each) and the linear CRC of their
 // all-reference template bodies.
 void build_segments(dnaf_ctx* c) {
@@ -882,6 +955,7 @@ struct Sink {
     bool device_only = false;
     bool pinned = false;     // buf is page-locked host memory
     int fd = -1;             // file descriptor mode: write() straight from the page-locked staging buffer
+    int64_t fd_off = -1;     // >= 0: pwrite() at this file offset instead (advanced as pieces land)
     bool log = false;        // append the blocks to the context's block log as they reach the host
 };
 
@@ -916,13 +990,15 @@ int deliver(dnaf_ctx* c, Sink& s, const uint8_t* data, uint64_t n) {
     if (s.fd >= 0) {
         uint64_t done = 0;
         while (done < n) {
-            const ssize_t w = ::write(s.fd, data + done, (size_t)std::min<uint64_t>(n - done, 1u << 30));
+            const size_t piece = (size_t)std::min<uint64_t>(n - done, 1u << 30);
+            const ssize_t w = s.fd_off >= 0 ? ::pwrite(s.fd, data + done, piece, (off_t)(s.fd_off + (int64_t)done)) : ::write(s.fd, data + done, piece);
             if (w < 0) {
                 if (errno == EINTR) continue;
                 return fail(c, DNAF_E_SINK, "write to file descriptor %d failed: %s", s.fd, strerror(errno));
             }
             done += (uint64_t)w;
         }
+        if (s.fd_off >= 0) s.fd_off += (int64_t)n;
     } else if (s.fn) {
         if (s.fn(s.user, data, n) != 0) return fail(c, DNAF_E_SINK, "sink callback failed");
     } else if (s.buf) {
@@ -1158,15 +1234,15 @@ uint64_t next_chunk_end(const dnaf_ctx* c, uint64_t r0, uint64_t row_end, uint64
     return std::min(r1, row_end);
 }
 
-int generate_passes(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t seed, int rng_mode, int level,
+int generate_passes(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t seed, int level,
                     Sink& sink, dnaf_stats* st);
 
 // The pass pipeline keeps up to three passes in flight.  When a call fails half way (sink error, caller's buffer
 // too small, CUDA error) nothing of it may still be running when the error is returned: a copy could be landing in a
 // caller buffer that is about to be freed, and the next call must find an idle pipeline.
-int generate_impl(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t seed, int rng_mode, int level,
+int generate_impl(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t seed, int level,
                   Sink& sink, dnaf_stats* st) {
-    const int rc = generate_passes(c, row_begin, row_end, seed, rng_mode, level, sink, st);
+    const int rc = generate_passes(c, row_begin, row_end, seed, level, sink, st);
     if (rc && c) {
         cudaSetDevice(c->dev);
         cudaStreamSynchronize(c->stream);   // may be the caller's stream (dnaf_set_stream), NULL = the default stream
@@ -1178,15 +1254,19 @@ int generate_impl(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t se
     return rc;
 }
 
-int generate_passes(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t seed, int rng_mode, int level,
+int generate_passes(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t seed, int level,
                     Sink& sink, dnaf_stats* st) {
     if (!c) return DNAF_E_ARG;
-    if (rng_mode != 0 && rng_mode != 1) return fail(c, DNAF_E_ARG, "rng_mode must be 0 (replay) or 1 (native)");
     if (level < 1 || level > 9) return fail(c, DNAF_E_ARG, "level must be 1..9");
     int rc = ensure_layout(c);
     if (rc) return rc;
     if (row_begin > row_end || row_end > c->S) return fail(c, DNAF_E_ARG, "row range out of bounds");
     CU(c, cudaSetDevice(c->dev));
+    // -z 1..3: the byte-4-back parse (k_auto); -z 4..9: LZ77 tiers of growing search depth (k_lz) on autosome rows
+    static const int lz_off = getenv("DNAF_NO_LZ") ? 1 : 0;
+    rc = ensure_lz_tables(c, lz_off ? 1 : level);
+    if (rc) return rc;
+    const bool use_lz = c->lz_ok;
     dnaf_stats local;
     memset(&local, 0, sizeof local);
     sink.log = c->log_blocks && !sink.device_only;
@@ -1346,8 +1426,24 @@ int generate_passes(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t 
             fa.sizes = c->sbuf[c->sb].sizes.as<uint32_t>();
             fa.crcs = c->sbuf[c->sb].crcs.as<uint32_t>();
             CU(c, cudaEventRecord(B.ev_auto[0], c->stream));
-            k_auto<<<c->implicit_pass ? c->pass_blocks : (uint32_t)c->fplan.size(), c->fused_threads, auto_smem_bytes(c->fused_threads),
-                     c->stream>>>(fa);
+            const uint32_t ablocks = c->implicit_pass ? c->pass_blocks : (uint32_t)c->fplan.size();
+            if (use_lz) {
+                const uint32_t smem = lz_smem_bytes(c->fused_threads, kLzMaxKey + 1u);
+                if (!c->lz_attr_done) {
+                    CU(c, cudaFuncSetAttribute(k_lz, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lz_smem_bytes(256, kLzMaxKey + 1u)));
+                    c->lz_attr_done = true;
+                }
+                LzArgs la;
+                la.a = fa;
+                la.tables = c->d_ltables.as<LzTable>();
+                const LzCfg cfg = lz_cfg(level, kLzMaxKey);
+                la.chain = cfg.chain;
+                la.lazy = cfg.lazy;
+                la.nice = cfg.nice;
+                k_lz<<<ablocks, c->fused_threads, smem, c->stream>>>(la);
+            } else {
+                k_auto<<<ablocks, c->fused_threads, auto_smem_bytes(c->fused_threads), c->stream>>>(fa);
+            }
             CU(c, cudaEventRecord(B.ev_auto[1], c->stream));
             if (c->implicit_pass) {
                 B.auto_text = c->pass_text;
@@ -1790,6 +1886,22 @@ int dnaf_bgzf_scan(const uint8_t* data, uint64_t n_bytes, uint32_t* csize, uint3
     return k > cap && (csize || usize) ? DNAF_E_SPACE : DNAF_OK;
 }
 
+int64_t dnaf_debug_lz_block(double p_minor, int level, const uint32_t* allele_bits, uint32_t n_cells, const uint8_t* prefix,
+                            uint32_t prefix_len, int ends_row, uint8_t* out, uint64_t out_cap) {
+    if (level < 4 || level > 9 || !allele_bits || !out || n_cells == 0 || n_cells > 254u * 64u || prefix_len > 64 ||
+        (prefix_len && !prefix))
+        return DNAF_E_ARG;
+    uint64_t hist[256] = {0};
+    for (uint32_t i = 0; i < prefix_len; ++i) hist[prefix[i]] += 16;
+    const int per_block = (int)((n_cells + 63u) / 64u);
+    const LzTable t = hosttab::make_lz_table(p_minor, prefix_len ? hist : nullptr, per_block, prefix_len != 0, level);
+    if (t.hdr_bits == 0xFFFFFFFFu) return DNAF_E_INPUT;
+    const std::vector<uint8_t> enc = hosttab::lz_encode_block_host(t, allele_bits, n_cells, prefix, prefix_len, ends_row != 0, level);
+    if (enc.size() > out_cap) return DNAF_E_SPACE;
+    memcpy(out, enc.data(), enc.size());
+    return (int64_t)enc.size();
+}
+
 int dnaf_bgzf_eof(uint8_t* out28) {
     static const uint8_t eof[28] = {0x1f, 0x8b, 0x08, 0x04, 0, 0, 0, 0, 0, 0xff, 0x06, 0x00, 0x42, 0x43,
                                     0x02, 0x00, 0x1b, 0x00, 0x03, 0,    0, 0,    0,    0,    0,    0,    0, 0};
@@ -1820,41 +1932,52 @@ int dnaf_row_offsets(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t
     return DNAF_OK;
 }
 
-int dnaf_generate(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t seed, int rng_mode, int level,
+int dnaf_generate(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t seed, int level,
                   uint8_t* out, uint64_t out_cap, dnaf_stats* stats) {
     if (!c) return DNAF_E_ARG;
     if (!out && out_cap) return fail(c, DNAF_E_ARG, "out is NULL");
     Sink s;
     s.buf = out;
     s.cap = out_cap;
-    return generate_impl(c, row_begin, row_end, seed, rng_mode, level, s, stats);
+    return generate_impl(c, row_begin, row_end, seed, level, s, stats);
 }
 
-int dnaf_generate_stream(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t seed, int rng_mode, int level,
+int dnaf_generate_stream(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t seed, int level,
                          dnaf_sink_fn sink, void* user, dnaf_stats* stats) {
     if (!c) return DNAF_E_ARG;
     if (!sink) return fail(c, DNAF_E_ARG, "sink is NULL");
     Sink s;
     s.fn = sink;
     s.user = user;
-    return generate_impl(c, row_begin, row_end, seed, rng_mode, level, s, stats);
+    return generate_impl(c, row_begin, row_end, seed, level, s, stats);
 }
 
-int dnaf_generate_fd(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t seed, int rng_mode, int level, int fd,
+int dnaf_generate_fd(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t seed, int level, int fd,
                      dnaf_stats* stats) {
     if (!c) return DNAF_E_ARG;
     if (fd < 0) return fail(c, DNAF_E_ARG, "bad file descriptor");
     Sink s;
     s.fd = fd;
-    return generate_impl(c, row_begin, row_end, seed, rng_mode, level, s, stats);
+    return generate_impl(c, row_begin, row_end, seed, level, s, stats);
 }
 
-int dnaf_generate_device(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t seed, int rng_mode, int level,
+int dnaf_generate_fd_at(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t seed, int level, int fd, uint64_t file_offset,
+                        dnaf_stats* stats) {
+    if (!c) return DNAF_E_ARG;
+    if (fd < 0) return fail(c, DNAF_E_ARG, "bad file descriptor");
+    if (file_offset > (uint64_t)INT64_MAX) return fail(c, DNAF_E_ARG, "file offset out of range");
+    Sink s;
+    s.fd = fd;
+    s.fd_off = (int64_t)file_offset;
+    return generate_impl(c, row_begin, row_end, seed, level, s, stats);
+}
+
+int dnaf_generate_device(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t seed, int level,
                          dnaf_stats* stats) {
     if (!c) return DNAF_E_ARG;
     Sink s;
     s.device_only = true;
-    return generate_impl(c, row_begin, row_end, seed, rng_mode, level, s, stats);
+    return generate_impl(c, row_begin, row_end, seed, level, s, stats);
 }
 
 int dnaf_genotypes(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t seed, uint8_t* out, uint64_t cap) {

@@ -8,6 +8,7 @@
 #pragma once
 #include <algorithm>
 #include <cstdint>
+#include <cmath>
 #include <cstring>
 #include <queue>
 #include <vector>
@@ -16,6 +17,7 @@
 #include "k_auto.cuh"
 #include "k_fused_text.cuh"
 #include "k_x.cuh"
+#include "k_lz.cuh"
 
 namespace dnaf {
 namespace hosttab {
@@ -526,6 +528,232 @@ inline FusedTable make_text_table(int cls, double p_minor, const uint8_t* sex, u
     for (size_t i = 0; i < hdr.words.size() && i < 62; ++i) t.hdr[i] = hdr.words[i];
     if (hdr.words.size() > 62) t.hdr_bits = 0xFFFFFFFFu;
     return t;
+}
+
+// ---- k_lz (k_lz.cuh): the LZ tiers' chains on the host, token statistics under lz_span_tokens, code tables ----
+// Host twin of the shared-memory structures k_lz builds per block: allele bits, prev[] and the per-region heads.
+struct LzHostMem {
+    std::vector<uint32_t> bits;     // + guard words
+    std::vector<uint16_t> prv;
+    std::vector<uint16_t> hd;       // [region][2^(key+1)]
+    uint32_t hbits = 0;
+    uint32_t word(uint32_t i) const { return bits[i]; }
+    uint32_t prev(uint32_t a) const { return prv[a]; }
+    uint32_t head(uint32_t reg, uint32_t key) const { return hd[((size_t)reg << hbits) + key]; }
+    // bits must hold (nall + 31) / 32 words; links every position whose key fits into its region's chain, in order
+    void build(uint32_t nall, uint32_t key_alleles) {
+        const uint32_t words = (nall + 31u) / 32u;
+        bits.resize(words + 8u, 0u);
+        for (uint32_t i = words; i < words + 8u; ++i) bits[i] = 0u;
+        if (nall & 31u) bits[words - 1u] &= (1u << (nall & 31u)) - 1u;
+        hbits = key_alleles + 1u;
+        const uint32_t nreg = (nall + kLzRegion - 1u) / kLzRegion;
+        prv.assign((size_t)nreg * kLzRegion, (uint16_t)kLzNone);
+        hd.assign((size_t)nreg << hbits, (uint16_t)kLzNone);
+        const uint32_t kmask = (1u << key_alleles) - 1u;
+        for (uint32_t a = 0; a + key_alleles <= nall; ++a) {
+            const uint32_t w = a >> 5, sh = a & 31u;
+            const uint32_t key = (lz_fsr(bits[w], bits[w + 1u], sh) & kmask) | ((a & 1u) << key_alleles);
+            uint16_t& h = hd[((size_t)(a / kLzRegion) << hbits) + key];
+            prv[a] = h;
+            h = (uint16_t)a;
+        }
+    }
+};
+
+struct LzHist {
+    uint64_t nlit[8] = {0};
+    uint64_t nlen[29] = {0};
+    uint64_t ndist[30] = {0};
+    uint64_t extra = 0;
+    void lit(int id) { nlit[id]++; }
+    void match(int len, int dist) {
+        const int li = len_index(len);
+        nlen[li]++;
+        uint32_t sym, eb, ev;
+        lz_dist_sym((uint32_t)dist, sym, eb, ev);
+        ndist[sym]++;
+        extra += (uint64_t)kLenExtra[li] + eb;
+    }
+    void eob() {}
+};
+
+// Token statistics of `blocks` blocks of `per_block` full spans of Bernoulli(p_minor) alleles under the LZ grammar.
+inline LzHist simulate_lz(double p_minor, int blocks, int per_block, bool starts_row, const LzCfg cfg) {
+    LzHist h;
+    uint64_t st = 0x9E3779B97F4A7C15ull ^ (uint64_t)(p_minor * 1e9);
+    auto next = [&]() {
+        st ^= st << 13; st ^= st >> 7; st ^= st << 17;
+        return st;
+    };
+    const uint64_t thr = (uint64_t)(std::min(p_minor, 0.999999) * 18446744073709551615.0);
+    LzHostMem mem;
+    const uint32_t nall = 128u * (uint32_t)per_block;
+    for (int b = 0; b < blocks; ++b) {
+        mem.bits.assign(4u * per_block + 8u, 0u);
+        for (int w = 0; w < 4 * per_block; ++w) {
+            uint32_t v = 0;
+            for (int i = 0; i < 32; ++i) v |= (uint32_t)(next() < thr) << i;
+            mem.bits[w] = v;
+        }
+        mem.build(nall, cfg.key);
+        for (int sp = 0; sp < per_block; ++sp)
+            lz_span_tokens(mem, 128u * sp, 64, sp == 0, starts_row, false, sp + 1 == per_block, nall, cfg, h);
+    }
+    return h;
+}
+
+// BFINAL=1, BTYPE=2 header for literal/length lengths `ll` (286) and distance lengths `dl` (30).
+inline BitString dynamic_header2(const std::vector<uint8_t>& ll, const std::vector<uint8_t>& dl) {
+    static const int order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+    int nlit = 286, ndist = 30;
+    while (nlit > 257 && ll[nlit - 1] == 0) --nlit;
+    while (ndist > 1 && dl[ndist - 1] == 0) --ndist;
+    std::vector<uint8_t> seq(ll.begin(), ll.begin() + nlit);
+    seq.insert(seq.end(), dl.begin(), dl.begin() + ndist);
+    std::vector<std::pair<int, int>> rl;  // (symbol, extra)
+    for (size_t i = 0; i < seq.size();) {
+        const int v = seq[i];
+        size_t run = 1;
+        while (i + run < seq.size() && seq[i + run] == v) ++run;
+        i += run;
+        if (v == 0) {
+            while (run >= 11) { const size_t c = std::min<size_t>(run, 138); rl.push_back({18, (int)c - 11}); run -= c; }
+            if (run >= 3) { rl.push_back({17, (int)run - 3}); run = 0; }
+            while (run-- > 0) rl.push_back({0, 0});
+        } else {
+            rl.push_back({v, 0});
+            --run;
+            while (run >= 3) { const size_t c = std::min<size_t>(run, 6); rl.push_back({16, (int)c - 3}); run -= c; }
+            while (run-- > 0) rl.push_back({v, 0});
+        }
+    }
+    std::vector<uint64_t> clf(19, 0);
+    for (auto& p : rl) clf[p.first]++;
+    std::vector<uint8_t> cll = huff_lengths(clf, 7);
+    int used = 0, only = 0;
+    for (int i = 0; i < 19; ++i)
+        if (cll[i]) { ++used; only = i; }
+    if (used == 1) cll[only == 0 ? 1 : 0] = 1;
+    std::vector<uint32_t> clc = huff_codes(cll);
+    int ncl = 19;
+    while (ncl > 4 && cll[order[ncl - 1]] == 0) --ncl;
+    BitString bs;
+    bs.put(1, 1);
+    bs.put(2, 2);
+    bs.put(nlit - 257, 5);
+    bs.put(ndist - 1, 5);
+    bs.put(ncl - 4, 4);
+    for (int i = 0; i < ncl; ++i) bs.put(cll[order[i]], 3);
+    for (auto& p : rl) {
+        bs.put(clc[p.first] & 0xFFFFFFu, (int)(clc[p.first] >> 24));
+        if (p.first == 16) bs.put(p.second, 2);
+        else if (p.first == 17) bs.put(p.second, 3);
+        else if (p.first == 18) bs.put(p.second, 7);
+    }
+    return bs;
+}
+
+// estimated payload bits of a histogram under its own optimal codes (for choosing the key length of a bucket)
+inline double lz_hist_bits(const LzHist& h) {
+    auto ent = [](const uint64_t* f, int n) {
+        double tot = 0, bits = 0;
+        for (int i = 0; i < n; ++i) tot += (double)f[i];
+        for (int i = 0; i < n; ++i)
+            if (f[i]) bits -= (double)f[i] * std::log2((double)f[i] / tot);
+        return bits;
+    };
+    uint64_t ll[37];
+    for (int i = 0; i < 8; ++i) ll[i] = h.nlit[i];
+    for (int i = 0; i < 29; ++i) ll[8 + i] = h.nlen[i];
+    return ent(ll, 37) + ent(h.ndist, 30) + (double)h.extra;
+}
+
+// Key length of a MAF bucket: rare minor alleles want long keys (few, long matches), common ones short keys.
+inline uint32_t lz_key_for(double p_minor) {
+    const double p = std::min(p_minor, 1.0 - p_minor);
+    return p < 0.12 ? 10u : (p < 0.22 ? 9u : 8u);
+}
+
+inline LzTable make_lz_table(double p_minor, const uint64_t* prefix_hist, int per_block, bool starts_row, int level) {
+    const int kBlocks = std::max(2, 512 / std::max(1, per_block));
+    const LzCfg cfg = lz_cfg(level, lz_key_for(p_minor));
+    const LzHist h = simulate_lz(p_minor, kBlocks, std::max(1, per_block), starts_row, cfg);
+    std::vector<uint64_t> f(286, 0), fd(30, 0);
+    const uint8_t lit_byte[5] = {'0', '1', '/', '\t', '\n'};
+    const uint64_t scale = 16, blocks = (uint64_t)kBlocks;
+    for (int i = 0; i < 5; ++i) f[lit_byte[i]] += (h.nlit[i] * scale) / blocks + 1;
+    for (int i = 0; i < 29; ++i) f[257 + i] += (h.nlen[i] * scale) / blocks + 1;
+    f[256] = scale;
+    if (prefix_hist)
+        for (int c = 0; c < 256; ++c)
+            if (prefix_hist[c]) f[c] += std::max<uint64_t>(1, prefix_hist[c]);
+    // every distance a block can need is a multiple of 4 up to 32768: symbols 3 and 5..29
+    for (int i = 3; i < 30; ++i)
+        if (i != 4) fd[i] = (h.ndist[i] * scale) / blocks + 1;
+    std::vector<uint8_t> ll = huff_lengths(f, 15), dl = huff_lengths(fd, 15);
+    std::vector<uint32_t> lc = huff_codes(ll), dc = huff_codes(dl);
+    LzTable t;
+    memset(&t, 0, sizeof t);
+    for (int len = 3; len <= 258; ++len) {
+        const int ci = len_index(len);
+        const uint32_t c = lc[257 + ci];
+        const uint32_t cl = c >> 24, ex = (uint32_t)kLenExtra[ci];
+        t.len_tok[len] = ((c & 0xFFFFFFu) | ((uint32_t)(len - kLenBase[ci]) << cl)) | ((cl + ex) << 24);
+    }
+    for (int i = 0; i < 5; ++i) t.lit[i] = lc[lit_byte[i]];
+    t.eob = lc[256];
+    for (int i = 0; i < 30; ++i) t.dist_tok[i] = dc[i];
+    t.key_alleles = cfg.key;
+    for (int c = 0; c < 256; ++c) t.pre_lit[c] = lc[c];
+    BitString hdr = dynamic_header2(ll, dl);
+    t.hdr_bits = hdr.bits;
+    for (size_t i = 0; i < hdr.words.size() && i < 96; ++i) t.hdr[i] = hdr.words[i];
+    if (hdr.words.size() > 96) t.hdr_bits = 0xFFFFFFFFu;
+    return t;
+}
+
+// Host-side deflate block of one autosome segment under an LzTable (self-test of grammar + codes + header; the
+// product path is k_lz).  bits: the block's allele bits; returns the raw deflate bytes.
+struct LzBitSink {
+    BitString bs;
+    const LzTable& t;
+    explicit LzBitSink(const LzTable& tt) : t(tt) {}
+    void tok(uint32_t v) { bs.put(v & 0xFFFFFFu, (int)(v >> 24)); }
+    void lit(int id) { tok(t.lit[id]); }
+    void match(int len, int dist) {
+        tok(t.len_tok[len]);
+        uint32_t sym, eb, ev;
+        lz_dist_sym((uint32_t)dist, sym, eb, ev);
+        tok(t.dist_tok[sym]);
+        bs.put(ev, (int)eb);
+    }
+    void eob() { tok(t.eob); }
+};
+
+inline std::vector<uint8_t> lz_encode_block_host(const LzTable& t, const uint32_t* bits, uint32_t ncells, const uint8_t* prefix,
+                                                 uint32_t plen, bool ends_row, int level) {
+    LzHostMem mem;
+    const uint32_t nall = 2u * ncells;
+    mem.bits.assign(bits, bits + (nall + 31u) / 32u);
+    mem.build(nall, t.key_alleles);
+    LzBitSink sink(t);
+    for (uint32_t i = 0; i < (t.hdr_bits + 31u) / 32u; ++i) {
+        const uint32_t nb = std::min(32u, t.hdr_bits - 32u * i);
+        sink.bs.put(t.hdr[i], (int)nb);
+    }
+    const bool starts_row = plen > 0;
+    for (uint32_t i = 0; i < plen; ++i) sink.tok(t.pre_lit[prefix[i]]);
+    const LzCfg cfg = lz_cfg(level, t.key_alleles);
+    const uint32_t nspans = (ncells + 63u) / 64u;
+    for (uint32_t sp = 0; sp < nspans; ++sp) {
+        const int nc = (int)std::min(64u, ncells - 64u * sp);
+        const bool last = sp + 1u == nspans;
+        lz_span_tokens(mem, 128u * sp, nc, sp == 0, starts_row, ends_row && last, last, nall, cfg, sink);
+    }
+    std::vector<uint8_t> out((sink.bs.bits + 7u) / 8u);
+    for (size_t i = 0; i < out.size(); ++i) out[i] = (uint8_t)(sink.bs.words[i >> 2] >> (8 * (i & 3)));
+    return out;
 }
 
 }  // namespace hosttab

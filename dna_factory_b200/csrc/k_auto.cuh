@@ -329,6 +329,98 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
     }
 }
 
+// The 128 allele bits of one span (64 cells from cell `cs`, nc of them real): replay-stream draws (dnaf_device.cuh) and the
+// forced-minor cells of the row (pop_factory.py:495-499).  Shared by k_auto and k_lz.
+__device__ __forceinline__ void auto_draw_span(const AutoArgs& a, const FusedDesc& d, uint32_t cs, int nc, uint32_t m[4]) {
+    if (nc > 0 && a.nv.k[d.row] == 2) {
+        const uint32_t thr = a.nv.thr[d.row * 4];
+        const uint64_t prow = a.row_base + d.row;
+        const uint32_t r_lo = (uint32_t)prow, r_hi = (uint32_t)(prow >> 32);
+        const uint32_t g0 = cs >> 4;
+        uint32_t eq[4], lt[4];
+        const int slots0 = (int)(2u * a.sv.n) - (int)(32u * g0);   // allele slots from this span's first group to the row's end
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            // lanes beyond the last sample start out decided ("U <= T": reference allele, mask bit 0)
+            eq[w] = __funnelshift_lc(0xFFFFFFFFu, 0u, (uint32_t)max(slots0 - 32 * w, 0));
+            lt[w] = ~eq[w];
+        }
+        // the first 8 bits of every lane decide 99.6 % of them: two calls per group, no divergence
+#pragma unroll
+        for (uint32_t q = 0; q < 2; ++q)
+#pragma unroll
+            for (int w = 0; w < 4; ++w) cmp_words(philox4x32_10(g0 + w, q, r_lo, r_hi, a.k0, a.k1), thr, 4u * q, eq[w], lt[w]);
+        // residual: one (group, call) per trip, whichever group of this thread still has an undecided lane
+        uint32_t qn = 0x02020202u;   // next call index per group, one byte each
+        for (;;) {
+            const int w = eq[0] ? 0 : (eq[1] ? 1 : (eq[2] ? 2 : (eq[3] ? 3 : 4)));
+            if (w == 4) break;
+            const uint32_t q = (qn >> (8 * w)) & 0xFFu;
+            uint32_t e = pick4(eq, w), l = pick4(lt, w);
+            cmp_words(philox4x32_10(g0 + w, q, r_lo, r_hi, a.k0, a.k1), thr, 4u * q, e, l);
+            if (q == 7u) {   // all 32 bits compared: lanes still equal have U == T, i.e. U <= T
+                l |= e;
+                e = 0;
+            }
+            qn += 1u << (8 * w);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (k == w) { eq[k] = e; lt[k] = l; }
+        }
+#pragma unroll
+        for (int w = 0; w < 4; ++w) m[w] = ~(lt[w] | eq[w]);   // U <= T -> reference allele
+    }
+    // forced-minor cells (pop_factory.py:495-499)
+    if (nc > 0) {
+        for (uint32_t o = 0; o < d.ovr_count; ++o) {
+            const uint32_t i = a.osamp[d.ovr_first + o];
+            if (i >= cs && i < cs + (uint32_t)nc) {
+                const uint32_t j = 2u * (i - cs);
+                const uint32_t bit = 3u << (j & 31u);
+#pragma unroll
+                for (int w = 0; w < 4; ++w)
+                    if ((j >> 5) == (uint32_t)w) m[w] |= bit;
+            }
+        }
+    }
+}
+
+// CRC32 share of one span: the span-local linear CRC of its allele mask, moved to the end of the block's cells.
+__device__ __forceinline__ uint32_t auto_span_crc(const AutoArgs& a, const FusedDesc& d, const uint32_t m[4], int nc, uint32_t tid,
+                                                  uint32_t nspans) {
+    // ---- CRC32 share of this span: template ^ delta (affine); delta's span-local CRC moved to the block end
+    uint32_t crc = 0;
+    const bool partial_tail = (d.ncells & 63u) != 0u;   // the block's last span is short
+    if (nc > 0 && (m[0] | m[1] | m[2] | m[3])) {
+        uint32_t mm[4] = {m[0], m[1], m[2], m[3]};
+        if (nc < 64) {  // partial last span: align its end with the table's span end (128-bit left shift)
+            const uint32_t sh = 2u * (64u - (uint32_t)nc);
+            const uint32_t ws = sh >> 5, bs = sh & 31u;
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                if (ws > (uint32_t)k) { mm[3] = mm[2]; mm[2] = mm[1]; mm[1] = mm[0]; mm[0] = 0; }
+            mm[3] = __funnelshift_l(mm[2], mm[3], bs);
+            mm[2] = __funnelshift_l(mm[1], mm[2], bs);
+            mm[1] = __funnelshift_l(mm[0], mm[1], bs);
+            mm[0] = mm[0] << bs;
+        }
+        uint32_t sp = 0;
+#pragma unroll
+        for (int w = 0; w < 4; ++w)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) sp ^= __ldg(&a.etab[(4 * w + k) * 256 + ((mm[w] >> (8 * k)) & 0xFFu)]);
+        // whole spans between the end of this span's cells and the end of the block's cells, then the short last span
+        const uint32_t last = nspans - 1u;
+        if (tid == last) crc = sp;                                   // ends where the cells end
+        else {
+            const uint32_t j = partial_tail ? last - 1u - tid : last - tid;
+            crc = j ? mul_tab(a.mtab + (size_t)j * 1024u, sp) : sp;
+            if (partial_tail) crc = mul_tab(a.mtail, crc);
+        }
+    }
+    return crc;
+}
+
 __global__ void __maxnreg__(56) k_auto(const AutoArgs a) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const uint32_t tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31u, wid = tid >> 5;
@@ -383,87 +475,8 @@ __global__ void __maxnreg__(56) k_auto(const AutoArgs a) {
     int nc = 0;
     if (tid < nspans) nc = (int)min(64u, d.ncells - 64u * tid);
     uint32_t m[4] = {0, 0, 0, 0};
-    if (nc > 0 && a.nv.k[d.row] == 2) {
-        const uint32_t thr = a.nv.thr[d.row * 4];
-        const uint64_t prow = a.row_base + d.row;
-        const uint32_t r_lo = (uint32_t)prow, r_hi = (uint32_t)(prow >> 32);
-        const uint32_t g0 = cs >> 4;
-        uint32_t eq[4], lt[4];
-        const int slots0 = (int)(2u * a.sv.n) - (int)(32u * g0);   // allele slots from this span's first group to the row's end
-#pragma unroll
-        for (int w = 0; w < 4; ++w) {
-            // lanes beyond the last sample start out decided ("U <= T": reference allele, mask bit 0)
-            eq[w] = __funnelshift_lc(0xFFFFFFFFu, 0u, (uint32_t)max(slots0 - 32 * w, 0));
-            lt[w] = ~eq[w];
-        }
-        // the first 8 bits of every lane decide 99.6 % of them: two calls per group, no divergence
-#pragma unroll
-        for (uint32_t q = 0; q < 2; ++q)
-#pragma unroll
-            for (int w = 0; w < 4; ++w) cmp_words(philox4x32_10(g0 + w, q, r_lo, r_hi, a.k0, a.k1), thr, 4u * q, eq[w], lt[w]);
-        // residual: one (group, call) per trip, whichever group of this thread still has an undecided lane
-        uint32_t qn = 0x02020202u;   // next call index per group, one byte each
-        for (;;) {
-            const int w = eq[0] ? 0 : (eq[1] ? 1 : (eq[2] ? 2 : (eq[3] ? 3 : 4)));
-            if (w == 4) break;
-            const uint32_t q = (qn >> (8 * w)) & 0xFFu;
-            uint32_t e = pick4(eq, w), l = pick4(lt, w);
-            cmp_words(philox4x32_10(g0 + w, q, r_lo, r_hi, a.k0, a.k1), thr, 4u * q, e, l);
-            if (q == 7u) {   // all 32 bits compared: lanes still equal have U == T, i.e. U <= T
-                l |= e;
-                e = 0;
-            }
-            qn += 1u << (8 * w);
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (k == w) { eq[k] = e; lt[k] = l; }
-        }
-#pragma unroll
-        for (int w = 0; w < 4; ++w) m[w] = ~(lt[w] | eq[w]);   // U <= T -> reference allele
-    }
-    // forced-minor cells (pop_factory.py:495-499)
-    if (nc > 0) {
-        for (uint32_t o = 0; o < d.ovr_count; ++o) {
-            const uint32_t i = a.osamp[d.ovr_first + o];
-            if (i >= cs && i < cs + (uint32_t)nc) {
-                const uint32_t j = 2u * (i - cs);
-                const uint32_t bit = 3u << (j & 31u);
-#pragma unroll
-                for (int w = 0; w < 4; ++w)
-                    if ((j >> 5) == (uint32_t)w) m[w] |= bit;
-            }
-        }
-    }
-    // ---- CRC32 share of this span: template ^ delta (affine); delta's span-local CRC moved to the block end
-    uint32_t crc = 0;
-    const bool partial_tail = (d.ncells & 63u) != 0u;   // the block's last span is short
-    if (nc > 0 && (m[0] | m[1] | m[2] | m[3])) {
-        uint32_t mm[4] = {m[0], m[1], m[2], m[3]};
-        if (nc < 64) {  // partial last span: align its end with the table's span end (128-bit left shift)
-            const uint32_t sh = 2u * (64u - (uint32_t)nc);
-            const uint32_t ws = sh >> 5, bs = sh & 31u;
-#pragma unroll
-            for (int k = 0; k < 3; ++k)
-                if (ws > (uint32_t)k) { mm[3] = mm[2]; mm[2] = mm[1]; mm[1] = mm[0]; mm[0] = 0; }
-            mm[3] = __funnelshift_l(mm[2], mm[3], bs);
-            mm[2] = __funnelshift_l(mm[1], mm[2], bs);
-            mm[1] = __funnelshift_l(mm[0], mm[1], bs);
-            mm[0] = mm[0] << bs;
-        }
-        uint32_t sp = 0;
-#pragma unroll
-        for (int w = 0; w < 4; ++w)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) sp ^= __ldg(&a.etab[(4 * w + k) * 256 + ((mm[w] >> (8 * k)) & 0xFFu)]);
-        // whole spans between the end of this span's cells and the end of the block's cells, then the short last span
-        const uint32_t last = nspans - 1u;
-        if (tid == last) crc = sp;                                   // ends where the cells end
-        else {
-            const uint32_t j = partial_tail ? last - 1u - tid : last - tid;
-            crc = j ? mul_tab(a.mtab + (size_t)j * 1024u, sp) : sp;
-            if (partial_tail) crc = mul_tab(a.mtail, crc);
-        }
-    }
+    auto_draw_span(a, d, cs, nc, m);
+    uint32_t crc = auto_span_crc(a, d, m, nc, tid, nspans);
     // prefix literal of this thread (blocks that start a row)
     uint32_t pre_tok = 0;
     if (tid < plen) pre_tok = __ldg(&tb->pre_lit[a.nv.prefix[pb + tid]]);

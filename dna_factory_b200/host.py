@@ -109,26 +109,47 @@ def override_pairs(fam_data, snps, row_base=0):
 def override_pairs_table(fam_data, table, row_base=0):
     """override_pairs for a SnpTable (integer ids): same membership semantics, no per-SNP Python objects.
     A key matches a row when `row_id in {key: ...}` would, i.e. when the key is a number equal to the id
-    (string keys of a deleterious.json replay never equal an int id)."""
-    ids = table.ids
+    (string keys of a deleterious.json replay never equal an int id).  One pass collects the (sample, key) pairs,
+    the id lookup is a single vectorised searchsorted."""
+    def numeric(key):
+        return (not isinstance(key, bool)) and isinstance(key, (int, float, np.integer, np.floating)) and key == int(key)
+
+    pairs = [(i, int(key)) for i, s in enumerate(fam_data) if not s.is_control and s.deleterious_snps
+             for key in s.deleterious_snps.keys() if numeric(key)]
+    if not pairs:
+        return np.zeros(0, np.uint64), np.zeros(0, np.uint32)
+    samp = np.fromiter((p[0] for p in pairs), dtype=np.int64, count=len(pairs))
+    keys = np.fromiter((p[1] for p in pairs), dtype=np.int64, count=len(pairs))
+    ids = np.asarray(table.ids, dtype=np.int64)
     order = np.argsort(ids, kind="stable")
     sorted_ids = ids[order]
-    rows, samples = [], []
-    for i, s in enumerate(fam_data):
-        if s.is_control or not s.deleterious_snps:
-            continue
-        for key in s.deleterious_snps.keys():
-            if isinstance(key, bool) or not isinstance(key, (int, float, np.integer, np.floating)) or key != int(key):
-                continue
-            lo = np.searchsorted(sorted_ids, int(key), side="left")
-            hi = np.searchsorted(sorted_ids, int(key), side="right")
-            for r in order[lo:hi]:
-                rows.append(row_base + int(r))
-                samples.append(i)
-    rows = np.asarray(rows, dtype=np.uint64)
-    samples = np.asarray(samples, dtype=np.uint32)
+    lo = np.searchsorted(sorted_ids, keys, side="left")
+    hi = np.searchsorted(sorted_ids, keys, side="right")
+    cnt = hi - lo                                            # rows carrying that id (1 for SnpFactory output)
+    tot = int(cnt.sum())
+    if tot == 0:
+        return np.zeros(0, np.uint64), np.zeros(0, np.uint32)
+    rep = np.repeat(np.arange(len(pairs)), cnt)
+    within = np.arange(tot) - np.repeat(np.cumsum(cnt) - cnt, cnt)
+    rows = (order[lo[rep] + within] + row_base).astype(np.uint64)
+    samples = samp[rep].astype(np.uint32)
     o = np.lexsort((samples, rows))
     return rows[o], samples[o]
+
+
+def slice_snps(arrays, lo, hi):
+    """Rows [lo, hi) of flatten_snps() / SnpTable.device_arrays() output, as their own dnaf_set_snps arguments."""
+    p0, p1 = int(arrays["prefix_off"][lo]), int(arrays["prefix_off"][hi])
+    return dict(chrom_class=arrays["chrom_class"][lo:hi], n_alleles=arrays["n_alleles"][lo:hi],
+                thresholds=arrays["thresholds"][lo:hi],
+                prefix_bytes=np.concatenate([arrays["prefix_bytes"][p0:p1], np.zeros(1, np.uint8)]),
+                prefix_off=arrays["prefix_off"][lo:hi + 1] - np.uint64(p0))
+
+
+def slice_overrides(orow, osamp, lo, hi):
+    """Override pairs of rows [lo, hi), rows made local to the slice."""
+    a, b = np.searchsorted(orow, [lo, hi], side="left")
+    return (orow[a:b] - np.uint64(lo)).astype(np.uint64), osamp[a:b]
 
 
 def configure(engine, fam_data, snps):

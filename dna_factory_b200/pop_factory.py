@@ -26,7 +26,7 @@ from datetime import datetime
 
 import numpy
 
-from . import _native, host
+from . import _native, partition, host
 from .tabix import TabixBuilder
 from .snp import (CHROMOSOME_LIST, CHROMOSOME_MAX_POSITION, CHROMOSOME_PROB, SNPTuples, SnpFactory, SnpTable,  # noqa: F401
                   is_haploid, split_list, stripe_list)
@@ -364,52 +364,69 @@ class PopulationFactory:
         print("Finished write_vcf_snps chunk Elapsed time: {:0.4f} seconds".format(time.time() - t0))
 
     def _write_multi_gpu(self, sex, ctl, arrays, orow, osamp, n_rows, seed, level, file, gpus, index_rows=None):
-        """Contiguous SNP ranges per GPU, no collective: BGZF blocks concatenate, so every rank's stream is
-        spooled and appended in rank order."""
-        import tempfile
-        bounds = [n_rows * g // gpus for g in range(gpus + 1)]
-        spools = [tempfile.TemporaryFile(dir=self.population_dir) for _ in range(gpus)]
+        """Contiguous SNP ranges per GPU, no collective (the reference stripes SNPs over its workers the
+        same way, pop_factory.py:426).  BGZF blocks concatenate and the kernels are deterministic, so every rank
+        first SIZES its stream on the device (dnaf_generate_device: no host traffic), the exclusive sum of the sizes
+        gives every rank its offset in population.vcf.gz, and then all ranks pwrite() their streams side by side --
+        nothing is spooled or copied twice.  Every rank holds only its own slice of the SNP table; the Philox row
+        counter of its local row r is bounds[g] + r (dnaf_set_row_base)."""
+        bounds = partition.row_bounds(n_rows, gpus)
         errors = []
-        index, blocks, row_off = getattr(file, "index", None), [None] * gpus, [None]
+        index = getattr(file, "index", None)
+        blocks, row_off, sizes, engines = [None] * gpus, [None] * gpus, [0] * gpus, [None] * gpus
+        barrier = threading.Barrier(gpus)
+        file.flush()   # the header blocks must be in the file: the ranks write behind them
+        base = file._handle.tell()
+        fd = file._handle.fileno()
 
         def run(g):
             try:
-                with _native.Engine(g) as eng:
-                    eng.set_samples(sex, ctl)
-                    eng.set_snps(**arrays)
-                    eng.set_overrides(orow, osamp)
-                    # rank 0's stream goes straight behind the header; the others spool and are appended in rank order
-                    fd = file._handle.fileno() if g == 0 else spools[g].fileno()
-                    if index is not None:
-                        eng.block_log(True)
-                        if g == 0:
-                            row_off[0] = eng.row_offsets(0, n_rows)
-                    self.stats.append(eng.generate_fd(bounds[g], bounds[g + 1], seed, fd, level=level))
-                    if index is not None:
-                        blocks[g] = eng.block_log_get()
+                lo, hi = bounds[g], bounds[g + 1]
+                eng = engines[g] = _native.Engine(g)
+                eng.set_samples(sex, ctl)
+                eng.set_snps(**host.slice_snps(arrays, lo, hi))
+                eng.set_overrides(*host.slice_overrides(orow, osamp, lo, hi))
+                eng.set_row_base(lo)
+                if index is not None:
+                    row_off[g] = eng.row_offsets(0, hi - lo)
+                sizes[g] = eng.generate_device(0, hi - lo, seed, level=level)["bgzf_bytes"]
             except BaseException as e:  # noqa: re-raised on the caller's thread
                 errors.append(e)
+            try:
+                barrier.wait()      # every rank's size is known
+            except threading.BrokenBarrierError:
+                return
+            if errors:
+                return
+            try:
+                lo, hi = bounds[g], bounds[g + 1]
+                eng = engines[g]
+                if index is not None:
+                    eng.block_log(True)
+                st = eng.generate_fd_at(0, hi - lo, seed, fd, base + sum(sizes[:g]), level=level)
+                if st["bgzf_bytes"] != sizes[g]:
+                    raise RuntimeError("rank %d: stream is %d bytes, its sizing pass said %d" % (g, st["bgzf_bytes"], sizes[g]))
+                self.stats.append(st)
+                if index is not None:
+                    blocks[g] = eng.block_log_get()
+            except BaseException as e:  # noqa
+                errors.append(e)
 
-        file.flush()   # the header blocks must be in the file before rank 0 writes behind them
         threads = [threading.Thread(target=run, args=(g,)) for g in range(gpus)]
         for t in threads:
             t.start()
         for t in threads:
             t.join()
+        for eng in engines:
+            if eng is not None:
+                eng.close()
         if errors:
             raise errors[0]
-        for sp in spools[1:]:
-            sp.seek(0)
-            while True:
-                buf = sp.read(1 << 24)
-                if not buf:
-                    break
-                file._handle.write(buf)
-        file._handle.flush()
-        for sp in spools:
-            sp.close()
+        file._handle.seek(base + sum(sizes))      # the sink appends the EOF block behind the last rank's stream
         if index is not None:
-            index.add_rows(*index_rows, row_off[0])
+            off = numpy.concatenate([numpy.zeros(1, numpy.uint64)] +
+                                    [r[1:] + numpy.uint64(sum(int(q[-1]) for q in row_off[:g])) for g, r in enumerate(row_off)])
+            index.add_rows(*index_rows, off)
             for cs, us in blocks:
                 index.add_blocks(cs, us)
 

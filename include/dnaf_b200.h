@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DNAF_ABI_VERSION 4
+#define DNAF_ABI_VERSION 5
 #define DNAF_KMAX 4 /* alleles per SNP the device path handles (A,C,G,T); K=2 for SnpFactory output */
 
 /* chromosome classes -- the only thing is_haploid() (common/snp.py:102-109) looks at */
@@ -162,20 +162,29 @@ int dnaf_row_offsets(dnaf_ctx* ctx, uint64_t row_begin, uint64_t row_end, uint64
  * The hot path: rows [row_begin,row_end) -> genotype draws -> VCF text -> BGZF blocks.
  * Emits whole BGZF blocks that decompress to exactly the text of those rows (first block starts
  * and last block ends on a row boundary; no header, no EOF block -- the caller writes those).
- * rng_mode: 0 = replay, 1 = native; both use the same counter-based Philox stream.
- * level: the -z value, 1..9.
+ * There is ONE uniform stream, the counter-based Philox stream of DESIGN.md 3: what a "replay" of the reference is fed
+ * and what a production ("native") run draws are the same function of (seed, global row, allele slot); ABI 4's
+ * rng_mode argument selected nothing and is gone.
+ * level: the -z value the reference hands to BgzfWriter (pop_factory.py:403; default 6, :656-658).  1..3 = the
+ * byte-4-back parse (k_auto), 4..9 = LZ77 tiers of growing search depth on autosome rows (k_lz: hash chains of
+ * 1 / 4 / 16 / 16+lazy / 32+lazy / 128+lazy candidates).  The decompressed text does not depend on it.
  */
-int dnaf_generate(dnaf_ctx* ctx, uint64_t row_begin, uint64_t row_end, uint64_t seed, int rng_mode, int level,
+int dnaf_generate(dnaf_ctx* ctx, uint64_t row_begin, uint64_t row_end, uint64_t seed, int level,
                   uint8_t* out, uint64_t out_cap, dnaf_stats* stats);
-int dnaf_generate_stream(dnaf_ctx* ctx, uint64_t row_begin, uint64_t row_end, uint64_t seed, int rng_mode,
-                         int level, dnaf_sink_fn sink, void* user, dnaf_stats* stats);
+int dnaf_generate_stream(dnaf_ctx* ctx, uint64_t row_begin, uint64_t row_end, uint64_t seed, int level,
+                         dnaf_sink_fn sink, void* user, dnaf_stats* stats);
 /* Same work, every piece written to an open file descriptor (the ordered `file.write(line)` loop of
  * pop_factory.py:438-469 without a trip through the interpreter); the caller flushes its own buffers first. */
-int dnaf_generate_fd(dnaf_ctx* ctx, uint64_t row_begin, uint64_t row_end, uint64_t seed, int rng_mode, int level,
+int dnaf_generate_fd(dnaf_ctx* ctx, uint64_t row_begin, uint64_t row_end, uint64_t seed, int level,
                      int fd, dnaf_stats* stats);
+/* Same, written with pwrite() at file_offset (the descriptor's own position is neither used nor moved): ranks of a
+ * multi-GPU run that know their streams' sizes (a dnaf_generate_device pass gives bgzf_bytes) write one shared file
+ * side by side, in SNP order, without spooling (pop_factory.py:426 stripes SNPs over workers the same way). */
+int dnaf_generate_fd_at(dnaf_ctx* ctx, uint64_t row_begin, uint64_t row_end, uint64_t seed, int level, int fd,
+                        uint64_t file_offset, dnaf_stats* stats);
 /* Same work, output left in (and then discarded from) device memory: kernel-only timing. */
-int dnaf_generate_device(dnaf_ctx* ctx, uint64_t row_begin, uint64_t row_end, uint64_t seed, int rng_mode,
-                         int level, dnaf_stats* stats);
+int dnaf_generate_device(dnaf_ctx* ctx, uint64_t row_begin, uint64_t row_end, uint64_t seed, int level,
+                         dnaf_stats* stats);
 
 /* Parity gates. genotypes: out[(r*n_samples+i)*2+s] = allele index, 0xFF where the cell has no such
  * allele (second slot of a haploid cell, both slots of '.').  text: the uncompressed rows. */
@@ -202,6 +211,14 @@ int dnaf_bgzf_scan(const uint8_t* data, uint64_t n_bytes, uint32_t* csize, uint3
  * dnaf_block_log_get stay valid until the next dnaf_generate* / dnaf_block_log call on the context. */
 int dnaf_block_log(dnaf_ctx* ctx, int enable);
 int dnaf_block_log_get(dnaf_ctx* ctx, const uint32_t** csize, const uint32_t** usize, uint64_t* n_blocks);
+/* Self-test hook of the LZ tiers (-z 4..9; csrc/k_lz.cuh): host code, no context, no GPU.  Encodes ONE autosome
+ * segment -- n_cells cells given as allele bits (bit 2i / 2i+1 = first / second allele of cell i), with the row
+ * prefix when prefix_len > 0, ending in '\n' when ends_row -- with the span grammar and the static code tables the
+ * kernel uses for minor-allele probability p_minor, and returns the raw deflate bytes (or a negative DNAF_E_*).
+ * It exists so that the CPU test suite can inflate what the table builder and the grammar produce; the product
+ * path never calls it. */
+int64_t dnaf_debug_lz_block(double p_minor, int level, const uint32_t* allele_bits, uint32_t n_cells, const uint8_t* prefix,
+                            uint32_t prefix_len, int ends_row, uint8_t* out, uint64_t out_cap);
 /* The 28-byte BGZF end-of-file block BgzfWriter.close() appends. */
 int dnaf_bgzf_eof(uint8_t* out28);
 

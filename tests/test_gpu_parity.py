@@ -125,6 +125,58 @@ def test_fused_kernel_vs_oracle_and_generic(native, n, s, seed):
     assert st_f["bgzf_bytes"] < 1.10 * st_p["bgzf_bytes"] + 4096
 
 
+@pytest.mark.parametrize("n,s,seed", [(4096, 10, 51), (4160, 8, 52), (16256, 5, 53), (16257, 5, 54), (20000, 24, 55),
+                                      (33000, 6, 56), (100003, 4, 57)])
+def test_lz_tiers_decompress_to_the_oracle_rows(native, n, s, seed):
+    """-z 4..9 run the LZ77 kernel k_lz on autosome rows (pop_factory.py:403 hands -z to the writer): every level must
+    decompress to the oracle's rows, be deterministic (two runs, same bytes), and a deeper tier must not be larger."""
+    from oracle import oracle
+    case = synth_case(n, s, seed=seed, chroms=['1', '2', '1', '7', 'X', '22', 'Y'], n_del=40)
+    want, _ = oracle.rows(case.samples, case.snps, case.seed, 0, n_threads=4)
+    eng = _engine(native, case, chunk=8 << 20)
+    sizes = {}
+    for level in (3, 4, 5, 6, 7, 8, 9):
+        blob, st = eng.generate(0, s, case.seed, level=level)
+        text, blocks, _ = oracle.bgzf_decompress(blob)
+        assert text == want, "level %d" % level
+        assert blocks == st["bgzf_blocks"] and st["ms_fused"] > 0
+        again, _ = eng.generate(0, s, case.seed, level=level)
+        assert again == blob, "level %d is not deterministic" % level
+        sizes[level] = len(blob)
+    # a handful of rows: allow 1.5 % noise between neighbouring tiers (the large-sample check is bench.py's level_sweep)
+    assert all(sizes[b] <= 1.015 * sizes[a] for a, b in zip((3, 4, 5, 6, 7, 8), (4, 5, 6, 7, 8, 9))), sizes
+    assert sizes[9] <= sizes[4] <= sizes[3], sizes
+    if s >= 20:
+        assert sizes[6] < 0.85 * sizes[3], sizes
+
+
+@pytest.mark.parametrize("level", [4, 6, 9])
+def test_lz_tiers_dense_overrides(native, level):
+    """The dense forced-minor patterns of test_auto_kernel_dense_overrides_on_rare_rows through k_lz: spans that
+    overflow their staging words re-emit straight into the block, every symbol has a code."""
+    from oracle import oracle
+    from tests.cases import Snp, Sample
+    n, stride = 12345, 1
+    snps = [Snp(id=i + 1, chromosome='1', position=1000 * (i + 1), tuples=[("A", 1 - maf), ("C", 1.0)])
+            for i, maf in enumerate([0.005, 0.01, 0.02, 0.25, 0.495, 0.005])]
+    samples = []
+    for i in range(n):
+        ctl = i < n // 3
+        d = None
+        if not ctl:
+            d = {sn.id: 0.5 for sn in snps[:5]} if (i % stride == 0 and (i // 97) % 2 == 0) else {}
+            if n // 2 <= i < n // 2 + 70:
+                d[6] = 0.5
+        samples.append(Sample(family_id=i + 1, person_id=100001 + i, father_id=0, mother_id=0, sex=1 + (i & 1),
+                              is_control=ctl, deleterious_snps=d))
+    from types import SimpleNamespace
+    case = SimpleNamespace(name="dense", seed=0xD15EA5E, row_begin=0, samples=samples, snps=snps, text=None)
+    want, _ = oracle.rows(case.samples, case.snps, case.seed, 0, n_threads=4)
+    eng = _engine(native, case)
+    blob, st = eng.generate(0, len(snps), case.seed, level=level)
+    assert oracle.bgzf_decompress(blob)[0] == want
+
+
 @pytest.mark.parametrize("n,stride", [(8192, 2), (8200, 3), (20000, 7), (12345, 1)])
 def test_auto_kernel_dense_overrides_on_rare_rows(native, n, stride):
     """Forced-minor cells (pop_factory.py:495-499) in patterns the rare-MAF code tables never expect: byte patterns
@@ -362,7 +414,7 @@ def test_failed_calls_leave_a_usable_context(native):
     assert b"".join(got) == want
     small = np.empty(len(want) // 2, np.uint8)
     st = _native.Stats()
-    rc = eng._lib.dnaf_generate(eng._h, 0, 96, case.seed, 0, 2, small.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)),
+    rc = eng._lib.dnaf_generate(eng._h, 0, 96, case.seed, 2, small.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)),
                                 small.nbytes, ctypes.byref(st))
     assert rc == -4 and b"too small" in eng._lib.dnaf_last_error(eng._h)
     again, _ = eng.generate(0, 96, case.seed, level=2)

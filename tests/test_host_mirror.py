@@ -20,7 +20,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert declared == set(_native.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.dnaf_abi_version() == 4
+    assert lib.dnaf_abi_version() == 5
     assert _native.bgzf_eof() == bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
 
 
