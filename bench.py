@@ -15,6 +15,10 @@ a new row window (and every rank its own contiguous SNP range), so inputs never 
   e2e     calls/s through the public API with HOST buffers: every step uploads that step's SNP metadata
           (H2D) and receives the BGZF bytes in host memory (D2H) inside the timed region
   roofline / cpu_baseline: see DESIGN.md section 6
+Extra keys of the N = 1 line: value_sustained (>= 1 s of back-to-back device-only calls), level_sweep (-z 1..9: ratio,
+value, e2e on the C5 sample shape), cli_to_file (the drop-in CLI writing population.vcf.gz), allele_chi_square
+(dna_factory_b200/allele_stats.py), cpu_baseline (the UNMODIFIED reference CLI from oracle/_ref, `-n <cores-1>`),
+cpu_baseline_c1_full (BASELINE config 1 in full) and cpu_baseline_port (the C port).  N > 1: multi_gpu_parity.
 """
 import argparse
 import json
@@ -157,6 +161,115 @@ def cpu_reference_run(steps, warmup, budget_s=20.0):
             "text_bytes": text_bytes, "bgzf_bytes": comp_bytes}
 
 
+def _inflate_bgzf(blob):
+    """Decompressed bytes of a BGZF stream without EOF block (plain zlib, member by member)."""
+    import zlib
+    out, data = [], memoryview(blob)
+    while len(data):
+        d = zlib.decompressobj(31)
+        out.append(d.decompress(data))
+        data = data[len(data) - len(d.unused_data):]
+    return b"".join(out)
+
+
+def run_extras(eng, torch, stream, R, n_steps_total, arrays, orow, osamp, row_base, local_rank):
+    """Extra keys of the 1-GPU line (module docstring).  `eng` still holds the whole resident table."""
+    from dna_factory_b200 import _native, allele_stats
+    out = {}
+    n_rows = 2 * n_steps_total * R
+    n = N_CASES + N_CONTROLS
+    # ---- value_sustained: back-to-back device-only calls over the whole resident table for >= 1 s (the timed `value`
+    # region is a few tens of ms, during which the GPU never leaves its burst power state)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    eng.generate_device(0, n_rows, PHILOX_SEED, level=LEVEL)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    calls = 0
+    ev0.record(stream)
+    while time.perf_counter() - t0 < 1.2:
+        calls += eng.generate_device(0, n_rows, PHILOX_SEED, level=LEVEL)["calls"]
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    out["value_sustained"] = {"value": calls / (ev0.elapsed_time(ev1) * 1e-3), "unit": "calls/s", "seconds": ev0.elapsed_time(ev1) * 1e-3,
+                              "what": "dnaf_generate_device over %d resident rows x %d samples, repeated back to back, -z %d" % (n_rows, n, LEVEL)}
+    # ---- level_sweep: BASELINE config 5 (-z 1..9 on 20 000 samples), one window of rows per level
+    sweep_rows = min(n_rows, 4 * R)
+    out_buf = torch.empty(int(eng.plan(0, sweep_rows)[1]) + (1 << 20), dtype=torch.uint8, pin_memory=True).numpy()
+    sweep = {}
+    for lv in range(1, 10):
+        eng.generate_device(0, sweep_rows, PHILOX_SEED, level=lv)                  # the tier's tables are built here
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        st = eng.generate_device(0, sweep_rows, PHILOX_SEED, level=lv)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        st2 = eng.generate_into(0, sweep_rows, PHILOX_SEED, out_buf, level=lv)
+        dt = time.perf_counter() - t1
+        sweep[str(lv)] = {"ratio": st["text_bytes"] / st["bgzf_bytes"], "value": st["calls"] / (e0.elapsed_time(e1) * 1e-3),
+                          "e2e": st2["calls"] / dt, "bgzf_bytes_per_call": st["bgzf_bytes"] / st["calls"]}
+    out["level_sweep"] = {"rows": sweep_rows, "samples": n, "note": "value: device only; e2e: one call, BGZF bytes into pinned host memory "
+                          "(SNP table resident)", "levels": sweep}
+    # ---- the drop-in CLI writing a real population.vcf.gz (C2 shape, SNP axis cut to 65536 rows)
+    try:
+        out["cli_to_file"] = cli_to_file(65536)
+    except Exception as e:   # noqa: a full disk or a missing tmp dir must not cost the bench line
+        out["cli_to_file"] = {"error": "%s: %s" % (type(e).__name__, e)}
+    # ---- allele-frequency chi-square of the draws (north_star), >= 1e8 calls
+    out["allele_chi_square"] = allele_stats.chi_square_report(level=LEVEL, device=local_rank)
+    return out
+
+
+def cli_to_file(snps, level=LEVEL):
+    """`pop_factory -s 10000 -c 10000 -x <snps> -f 0.01 -z 2 --gpu_select` of the re-hosted CLI into a temp dir."""
+    import contextlib
+    import io
+    import shutil
+    import tempfile
+    from dna_factory_b200 import pop_factory
+    d = tempfile.mkdtemp(prefix="dnaf_cli_")
+    try:
+        buf = io.StringIO()
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(buf):
+            pop_factory.main(["-s", str(N_CASES), "-c", str(N_CONTROLS), "-x", str(snps), "-f", str(MIN_MAF), "-z", str(level), "-p",
+                              os.path.join(ROOT, "tests", "golden", "cli_small", "deleterious_config.yml"), "--outdir", d, "--seed", "123456", "--gpu_select"])
+        wall = time.perf_counter() - t0
+        import re
+        m = re.findall(r"Finished write_vcf_snps chunk Elapsed time: ([0-9.]+) seconds", buf.getvalue())
+        write_s = sum(float(x) for x in m)
+        calls = (N_CASES + N_CONTROLS) * snps
+        size = os.path.getsize(os.path.join(d, "population.vcf.gz"))
+        return {"calls_per_s_write_vcf_snps": calls / write_s if write_s else None, "calls_per_s_wall": calls / wall, "wall_s": wall,
+                "write_vcf_snps_s": write_s, "vcf_gz_bytes": size, "snps": snps, "samples": N_CASES + N_CONTROLS, "level": level}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
+def python_reference_run(steps, warmup, rows=600):
+    """The UNMODIFIED reference CLI (oracle/_ref, materialised by oracle/make_ref.py) on the host cores:
+    `pop_factory.py -s 10000 -c 10000 -x <rows> -f 0.01 -n <cores-1> -z 2`, one process run per step; the time of a
+    step is the reference's own write_vcf_snps timer (pop_factory.py:417)."""
+    from oracle import ref_cli
+    runs = [ref_cli.run(N_CONTROLS, N_CASES, rows, LEVEL, min_maf=MIN_MAF) for _ in range(steps + warmup)][warmup:]
+    total = sum(r["write_s"] for r in runs)
+    calls = sum(r["calls"] for r in runs)
+    return {"value": calls / total, "ms_per_step": 1e3 * total / len(runs), "cores": runs[0]["procs"] + 1, "procs": runs[0]["procs"],
+            "wall_s_per_step": sum(r["wall_s"] for r in runs) / len(runs),
+            "sample": "%d runs of the unmodified reference CLI `pop_factory.py -s %d -c %d -x %d -f %s -n %d -z %d` "
+                      "(C2 with the SNP axis cut from 5 000 000 to %d rows); time = its own write_vcf_snps timer lines" % (
+                          len(runs), N_CONTROLS, N_CASES, rows, MIN_MAF, runs[0]["procs"], LEVEL, rows)}
+
+
+def python_reference_c1():
+    """BASELINE config 1 in full through the unmodified reference CLI: -s 100 -c 100 -x 100000 -f 0.01 -z 2."""
+    from oracle import ref_cli
+    r = ref_cli.run(100, 100, 100000, LEVEL, min_maf=MIN_MAF)
+    return {"value": r["calls_per_s"], "unit": "calls/s", "cores": r["procs"] + 1, "kind": "reference", "write_vcf_snps_s": r["write_s"],
+            "wall_s": r["wall_s"], "vcf_bytes": r["vcf_bytes"],
+            "sample": "config 1 in full: pop_factory.py -s 100 -c 100 -x 100000 -f 0.01 -n %d -z %d (2e7 calls)" % (r["procs"], LEVEL)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -165,6 +278,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows-per-step", type=int, default=ROWS_PER_STEP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip level_sweep / value_sustained / cli_to_file / chi-square")
+    ap.add_argument("--level", type=int, default=LEVEL, help="-z of the timed steps (default: the workload's 2)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -174,12 +289,19 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        r = cpu_reference_run(args.steps, args.warmup)
+        from oracle import make_ref
+        make_ref.materialise()
+        if make_ref.available():
+            r = python_reference_run(args.steps, args.warmup)
+            kind = "reference"
+        else:
+            r = cpu_reference_run(args.steps, args.warmup)
+            kind = "port"
         line = {"impl": "reference", "metric": "genotype calls/sec to bgzf VCF", "value": r["value"],
                 "unit": "calls/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u32", "data": "synthetic", "config": {"workload": WORKLOAD},
-                "cpu_baseline": {"value": r["value"], "unit": "calls/s", "cores": r["cores"], "kind": "port",
+                "cpu_baseline": {"value": r["value"], "unit": "calls/s", "cores": r["cores"], "kind": kind,
                                  "sample": r["sample"]},
                 "e2e": {"value": r["value"], "unit": "calls/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
@@ -188,7 +310,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from dna_factory_b200 import _native, partition
+    from dna_factory_b200 import _native, host, partition
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: dna_factory_b200 has no CPU fallback")
@@ -229,14 +351,14 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     for k in range(warmup):
-        eng.generate_device(k * R, (k + 1) * R, PHILOX_SEED, level=LEVEL)
+        eng.generate_device(k * R, (k + 1) * R, PHILOX_SEED, level=args.level)
     barrier()
     sampler.mark_begin()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stats = []
     ev0.record(stream)
     for k in range(warmup, n_steps_total):
-        stats.append(eng.generate_device(k * R, (k + 1) * R, PHILOX_SEED, level=LEVEL))
+        stats.append(eng.generate_device(k * R, (k + 1) * R, PHILOX_SEED, level=args.level))
     ev1.record(stream)
     barrier()
     sampler.mark_end()
@@ -273,7 +395,7 @@ def main():
     auto_text = sum(s["auto_text_bytes"] for s in stats)
     auto_launches = sum(s["auto_launches"] for s in stats)
     if ms_auto > 0:
-        achieved, kernel = auto_text / (ms_auto * 1e-3) / 1e9, "k_auto"
+        achieved, kernel = auto_text / (ms_auto * 1e-3) / 1e9, ("k_auto" if args.level <= 3 else "k_lz")
     else:
         achieved, kernel = stage_achieved, dom.replace("ms_", "")
     roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -323,7 +445,7 @@ def main():
         e.set_snps(**a)
         e.set_overrides(o_r, o_s)
         e.set_row_base(row_base + lo)
-        return e.generate_into(0, R, PHILOX_SEED, outs[j], level=LEVEL)
+        return e.generate_into(0, R, PHILOX_SEED, outs[j], level=args.level)
 
     def run_steps(ks):
         """Steps ks, dealt round-robin to the contexts; every context runs its steps in order on its own thread."""
@@ -354,15 +476,75 @@ def main():
     d2h = int(np.mean([s["bgzf_bytes"] for s in e2e_stats]))
     launches += 0  # e2e launches are outside the `value` region
 
+
+    # ------------------------------------------------------------------ multi-GPU parity (N > 1)
+    # Every rank regenerates nothing on trust: it inflates a window at the START of its own SNP range (produced with
+    # its own row_base) and publishes (text bytes, blocks, CRC32 of the text); rank 0 recomputes every rank's window
+    # on ITS GPU with that rank's row base -- rows are a pure function of (seed, global row, sample) -- and checks the
+    # last rank's window against the CPU oracle as well.
+    multi_gpu_parity = None
+    if world > 1:
+        import zlib
+        W = 24
+        blob, st_w = eng.generate(0, W, PHILOX_SEED, level=args.level)
+        text = _inflate_bgzf(blob)
+        mine = torch.tensor([len(text), st_w["bgzf_blocks"], zlib.crc32(text), st_w["crc_xor"]], dtype=torch.int64, device="cuda")
+        allv = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allv, mine)
+        if rank == 0:
+            ok, why = True, ""
+            bounds = partition.row_bounds(TOTAL_SNPS, world)
+            for r in range(world):
+                sex_r, ctl_r, table_r, orow_r, osamp_r = synth_population(R, r, window=R)
+                chk = _native.Engine(local_rank)
+                chk.set_samples(sex_r, ctl_r)
+                chk.set_snps(**host.slice_snps(table_r.device_arrays(), 0, W))
+                chk.set_overrides(*host.slice_overrides(orow_r, osamp_r, 0, W))
+                chk.set_row_base(bounds[r])
+                b2, st2 = chk.generate(0, W, PHILOX_SEED, level=args.level)
+                t2 = _inflate_bgzf(b2)
+                got = [int(x) for x in allv[r].tolist()]
+                if got != [len(t2), st2["bgzf_blocks"], zlib.crc32(t2), st2["crc_xor"]]:
+                    ok, why = False, "rank %d window differs from its single-GPU recomputation" % r
+                if r == world - 1 and ok:
+                    from oracle import oracle
+                    from types import SimpleNamespace
+                    fam = [SimpleNamespace(sex=int(a), is_control=bool(c), deleterious_snps=None if c else {}, person_id=i)
+                           for i, (a, c) in enumerate(zip(sex_r, ctl_r))]
+                    flat = oracle.flatten(fam, [table_r.snp(q) for q in range(W)])
+                    o_r, o_s = host.slice_overrides(orow_r, osamp_r, 0, W)
+                    flat["over_row"], flat["over_sample"] = o_r, o_s
+                    want, _ = oracle.rows_from_flat(flat, PHILOX_SEED, bounds[r], n_threads=8)
+                    if want.tobytes() != t2:
+                        ok, why = False, "rank %d window differs from the CPU oracle" % r
+                chk.close()
+            multi_gpu_parity = "ok" if ok else "FAILED: " + why
+            if not ok:
+                raise SystemExit("multi-GPU parity check failed: " + why)
+
+    # ------------------------------------------------------------------ extras (rank 0 of a 1-GPU run)
+    extras = {}
+    if world == 1 and not args.no_extras:
+        extras = run_extras(eng, torch, stream, R, n_steps_total, arrays, orow, osamp, row_base, local_rank)
+
     if rank == 0:
         cpu = None
+        cpu_port = cpu_c1 = None
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_reference_run(6, 1)
-            cpu = {"value": r["value"], "unit": "calls/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+            cpu_port = {"value": r["value"], "unit": "calls/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+            cpu = cpu_port
+            from oracle import make_ref
+            make_ref.materialise()
+            if make_ref.available():      # the reference's own `-n <cores-1>` multiprocess path, same box, same run
+                r = python_reference_run(2, 0, rows=800)
+                cpu = {"value": r["value"], "unit": "calls/s", "cores": r["cores"], "kind": "reference", "sample": r["sample"],
+                       "worker_processes": r["procs"], "wall_s_per_run": r["wall_s_per_step"]}
+                cpu_c1 = python_reference_c1()
         line = {"metric": "genotype calls/sec to bgzf VCF", "value": value, "unit": "calls/s", "n_gpus": world,
                 "steps": args.steps, "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "samples": n, "rows_per_step": R, "level": LEVEL,
+                "config": {"workload": WORKLOAD, "samples": n, "rows_per_step": R, "level": args.level,
                            "l2_policy": "inputs larger than L2: each step draws a new %d MB text window" % (
                                text_bytes // len(stats) >> 20),
                            "partition": "contiguous SNP ranges per rank, no collective",
@@ -371,6 +553,13 @@ def main():
                         "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                 "compression_ratio": text_bytes / max(1, bgzf_bytes), "text_gb_per_s": text_bytes / (ms * 1e-3) / 1e9}
+        if cpu_port is not None:
+            line["cpu_baseline_port"] = cpu_port
+            line["cpu_baseline_python"] = cpu if cpu is not cpu_port else None
+            line["cpu_baseline_c1_full"] = cpu_c1
+        if multi_gpu_parity is not None:
+            line["multi_gpu_parity"] = multi_gpu_parity
+        line.update(extras)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -27,6 +27,7 @@ from datetime import datetime
 import numpy
 
 from . import _native, partition, host
+from . import tabix
 from .tabix import TabixBuilder
 from .snp import (CHROMOSOME_LIST, CHROMOSOME_MAX_POSITION, CHROMOSOME_PROB, SNPTuples, SnpFactory, SnpTable,  # noqa: F401
                   is_haploid, split_list, stripe_list)
@@ -339,6 +340,7 @@ class PopulationFactory:
         if index is not None:
             table = snps if isinstance(snps, SnpTable) else SnpTable.from_snps(snps)
             index_rows = (table.chrom_labels, table.chrom_idx, table.position)
+            tabix.validate_rows(table.chrom_idx, table.position)    # fail before the generation, not after it
         if gpus == 1:
             own = engine is None
             eng = engine or _native.Engine(0)
@@ -494,7 +496,8 @@ def parse_cmd_args(args):
 
 def main(sys_args):
     args = parse_cmd_args(sys_args)
-    if not args.generate_snps:
+    if not args.generate_snps and not args.snps_file:
+        # with --snps_file the reference never touches its database either (pop_factory.py:221-231)
         raise SystemExit("-l needs the reference's RefSNP database layer; use --snps_file with an exported snps.json.gz")
     factory = PopulationFactory(num_processes=args.num_processes, generate_snps=args.generate_snps,
                                 deleterious_list_path=args.deleterious_file, sample_id_offset=args.offset,

@@ -104,6 +104,25 @@ class TabixBuilder:
         return build_tbi(names, chrom, pos, virtual_offsets(start, cs, us), virtual_offsets(end, cs, us))
 
 
+def validate_rows(chrom_idx, position):
+    """What a .tbi index needs of the rows, checked BEFORE the (long) generation instead of after it: positions
+    within 0 .. 2^29, every chromosome's rows contiguous, positions sorted inside a chromosome.  Raises ValueError."""
+    chrom = np.asarray(chrom_idx, np.int64)
+    position = np.asarray(position, np.int64)
+    S = len(chrom)
+    if not S:
+        return
+    if int(position.min()) < 0 or int(position.max()) > MAX_POS:
+        raise ValueError("position outside what a .tbi index can address (0 .. 2^29)")
+    cut = np.flatnonzero(np.diff(chrom)) + 1
+    seen = chrom[np.concatenate(([0], cut))]
+    if len(np.unique(seen)) != len(seen):
+        raise ValueError("rows of one chromosome are not contiguous: the file cannot be tabix-indexed")
+    same = np.diff(chrom) == 0
+    if np.any(np.diff(np.maximum(position - 1, 0))[same] < 0):
+        raise ValueError("rows of a chromosome are not sorted by position: the file cannot be tabix-indexed")
+
+
 def build_tbi(names, chrom, position, voff_start, voff_end):
     """Uncompressed .tbi bytes.  `chrom[r]` indexes `names`; rows must be grouped by chromosome and sorted by
     position inside each (what tabix requires of the file; pop_factory.py:245 sorts that way)."""

@@ -98,8 +98,10 @@ int dnaf_set_samples(dnaf_ctx* ctx, uint32_t n_samples, const uint8_t* sex, cons
  *                    `tuples[k][1] >= u` (pop_factory.py:94) becomes the integer test U <= threshold
  *                    for u = U * 2^-32; entries k >= n_alleles are ignored
  *   prefix_bytes / prefix_off[r..r+1]  the 9-column row lead exactly as pop_factory.py:503-507 formats it
- * Returns DNAF_E_INPUT when the last threshold of a row is not saturated (the reference's
- * pick_allele_index would return None and "%i" would raise).
+ * The last allele of a row takes whatever its table leaves above the last cumulative probability.  Returns
+ * DNAF_E_INPUT when that last value is below 0.999 (a broken table: the reference's pick_allele_index would return
+ * None and "%i" would raise as soon as a roll lands there); values that merely round short of 1.0 are accepted with
+ * a one-line note on stderr.
  */
 int dnaf_set_snps(dnaf_ctx* ctx, uint64_t n_snps, const uint8_t* chrom_class, const uint8_t* n_alleles,
                   const uint32_t* thresholds, const uint8_t* prefix_bytes, const uint64_t* prefix_off);

@@ -227,7 +227,68 @@ def case_cli_small():
     print("cli_small      vcf=%d bytes, %d lines" % (len(vcf), vcf.count(b"\n")))
 
 
+def case_cli_offset():
+    """The README's multi-run recipe (README.md:88-94): a replay from snps.json.gz / deleterious.json with `--offset 300`
+    (pop_factory.py:350-351,378: control ids 100000+offset, case ids 500000+offset, family ids i+1+2*offset).  Pins
+    population.fam, pop_deleterious.txt and the VCF (header sample ids + rows) of the UNMODIFIED reference."""
+    ref = ref_harness.load()
+    out = os.path.join(HERE, "cli_offset")
+    src = os.path.join(HERE, "cli_small")
+    tmp = "/tmp/dnaf_golden_cli_offset"
+    shutil.rmtree(tmp, ignore_errors=True)
+    shutil.rmtree(out, ignore_errors=True)
+    os.makedirs(out)
+    os.makedirs(tmp)
+    philox_seed = 123456
+    parent = os.getpid()
+    state = {"k": 0}
+    real_rand = ref.numpy.random.rand
+
+    class FixedDatetime(ref.datetime):
+        @classmethod
+        def now(cls, tz=None):
+            return cls(2026, 1, 1, 12, 34, 56)
+
+    def rand(*shape):
+        if os.getpid() == parent:
+            return real_rand(*shape)
+        u = philox_np.uniforms(philox_seed, state["k"], shape[0])
+        state["k"] += 1
+        return u
+
+    snps_gz = os.path.join(tmp, "snps_in.json.gz")
+    with open(os.path.join(src, "snps.json"), "rb") as f, gzip.open(snps_gz, "wb") as g:
+        g.write(f.read())
+    base_args = ["-s", "6", "-c", "5", "-z", "2", "-m", "0.5", "-n", "1", "--offset", "300"]
+    args = base_args + ["--snps_file", snps_gz, "--deleterious_file", os.path.join(src, "deleterious.json"), "--outdir",
+                        os.path.join(tmp, "out")]
+    real_dt = ref.datetime
+    ref.datetime = FixedDatetime
+    ref.numpy.random.rand = rand
+    random.seed(777)
+    try:
+        ref.main(args)
+    finally:
+        ref.datetime = real_dt
+        ref.numpy.random.rand = real_rand
+    with gzip.open(os.path.join(tmp, "out", "population.vcf.gz"), "rb") as f:
+        vcf = f.read()
+    for name in ("population.fam", "pop_deleterious.txt"):
+        shutil.copy(os.path.join(tmp, "out", name), os.path.join(out, name))
+    with open(os.path.join(out, "population.vcf.rows.gz"), "wb") as raw:
+        with gzip.GzipFile(filename="", mode="wb", fileobj=raw, compresslevel=9, mtime=0) as f:
+            f.write(vcf)
+    with open(os.path.join(out, "meta.json"), "w") as f:
+        json.dump({"args": base_args, "numpy_seed": 123456, "python_random_seed": 777, "philox_seed": philox_seed,
+                   "filedate": "20260101 12:34", "inputs": "cli_small/snps.json (gzipped), cli_small/deleterious.json",
+                   "vcf_sha256": hashlib.sha256(vcf).hexdigest(), "vcf_len": len(vcf)}, f)
+    print("cli_offset     vcf=%d bytes, %d lines" % (len(vcf), vcf.count(b"\n")))
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["cli_offset"]:
+        case_cli_offset()
+        sys.exit(0)
     case_snp_select()
     case_mixed64()
     case_r8_strkeys()
@@ -235,3 +296,4 @@ if __name__ == "__main__":
     case_wide()
     case_single_sex()
     case_cli_small()
+    case_cli_offset()

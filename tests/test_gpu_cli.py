@@ -46,6 +46,35 @@ def test_cli_output_directory_matches_reference(tmp_path, monkeypatch, extra):
         assert (tmp_path / name).read_bytes() == open(os.path.join(gold, name), "rb").read(), name
 
 
+def test_cli_offset_replay_matches_reference(tmp_path, monkeypatch):
+    """The README's multi-run recipe (README.md:88-94): `--offset 300` replayed from snps.json.gz / deleterious.json.
+    population.fam, pop_deleterious.txt and the whole VCF (header ids + rows) against the pinned reference run
+    (tests/golden/cli_offset, pop_factory.py:350-351,378)."""
+    import hashlib
+    from dna_factory_b200 import pop_factory
+    gold = os.path.join(GOLDEN, "cli_offset")
+    src = os.path.join(GOLDEN, "cli_small")
+    meta = json.load(open(os.path.join(gold, "meta.json")))
+
+    class FixedDatetime(pop_factory.datetime):
+        @classmethod
+        def now(cls, tz=None):
+            return cls(2026, 1, 1, 12, 34, 56)
+
+    monkeypatch.setattr(pop_factory, "datetime", FixedDatetime)
+    snps_gz = tmp_path / "snps_in.json.gz"
+    with open(os.path.join(src, "snps.json"), "rb") as f, gzip.open(snps_gz, "wb") as g:
+        g.write(f.read())
+    random.seed(meta["python_random_seed"])
+    out = tmp_path / "out"
+    pop_factory.main(meta["args"] + ["--snps_file", str(snps_gz), "--deleterious_file", os.path.join(src, "deleterious.json"),
+                                     "--outdir", str(out), "--seed", str(meta["philox_seed"])])
+    vcf = gzip.decompress((out / "population.vcf.gz").read_bytes())
+    assert hashlib.sha256(vcf).hexdigest() == meta["vcf_sha256"] and len(vcf) == meta["vcf_len"]
+    for name in ("population.fam", "pop_deleterious.txt"):
+        assert (out / name).read_bytes() == open(os.path.join(gold, name), "rb").read(), name
+
+
 def test_cli_replay_from_files_reproduces_r8(tmp_path, monkeypatch):
     """--snps_file / --deleterious_file replay: string keys of deleterious.json never match the int ids, so
     no forced minors appear -- exactly what the reference does.  Checked against the oracle."""
