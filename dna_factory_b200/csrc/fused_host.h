@@ -540,7 +540,9 @@ struct LzHostMem {
     uint32_t word(uint32_t i) const { return bits[i]; }
     uint32_t prev(uint32_t a) const { return prv[a]; }
     uint32_t head(uint32_t reg, uint32_t key) const { return hd[((size_t)reg << hbits) + key]; }
-    // bits must hold (nall + 31) / 32 words; links every position whose key fits into its region's chain, in order
+    // bits must hold (nall + 31) / 32 words.  Same structure as the kernel builds: steps of 32 consecutive positions;
+    // every position of a step points at the key's last occurrence BEFORE the step, the step's last occurrence of a
+    // key becomes the head.
     void build(uint32_t nall, uint32_t key_alleles) {
         const uint32_t words = (nall + 31u) / 32u;
         bits.resize(words + 8u, 0u);
@@ -551,12 +553,16 @@ struct LzHostMem {
         prv.assign((size_t)nreg * kLzRegion, (uint16_t)kLzNone);
         hd.assign((size_t)nreg << hbits, (uint16_t)kLzNone);
         const uint32_t kmask = (1u << key_alleles) - 1u;
-        for (uint32_t a = 0; a + key_alleles <= nall; ++a) {
-            const uint32_t w = a >> 5, sh = a & 31u;
-            const uint32_t key = (lz_fsr(bits[w], bits[w + 1u], sh) & kmask) | ((a & 1u) << key_alleles);
-            uint16_t& h = hd[((size_t)(a / kLzRegion) << hbits) + key];
-            prv[a] = h;
-            h = (uint16_t)a;
+        uint32_t keys[32];
+        for (uint32_t pos = 0; pos < nall; pos += 32u) {
+            const uint32_t reg = pos / kLzRegion;
+            const uint32_t n = std::min(32u, ((nall + 31u) & ~31u) - pos);
+            for (uint32_t l = 0; l < n; ++l) {
+                const uint32_t a = pos + l, w = a >> 5, sh = a & 31u;
+                keys[l] = (lz_fsr(bits[w], bits[w + 1u], sh) & kmask) | ((a & 1u) << key_alleles);
+                prv[a] = hd[((size_t)reg << hbits) + keys[l]];
+            }
+            for (uint32_t l = n; l-- > 0;) hd[((size_t)reg << hbits) + keys[l]] = (uint16_t)(pos + l);   // descending: the step's FIRST occurrence stays
         }
     }
 };

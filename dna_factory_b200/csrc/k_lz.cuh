@@ -14,10 +14,14 @@
 // Match finder (deterministic, built per block in shared memory):
 //   * key of allele position a = its next L alleles (L <= 10, per MAF bucket) and a's parity (distances are even)
 //   * a block is cut into REGIONS of 4096 alleles = the 32 spans of one warp.  Every warp links the positions of its
-//     region into per-key chains in exact position order: 32 consecutive positions per step, __match_any_sync finds
-//     equal keys inside the step, head[region][key] carries the last occurrence across steps.  prev[a] = the previous
-//     position of the same key in the region.  No atomics, no dependence on scheduling: the same block always gives
-//     the same chains.
+//     region into per-key chains in position order, 32 consecutive positions per step: every lane reads
+//     head[region][key] (the last occurrence before this step) into prev[a], then the step's positions go into the
+//     heads with atomicMax.  Positions of one step that share a key all point at the same predecessor and only the
+//     last of them is reachable from later steps -- which thins exactly the over-populated keys (the inside of a long
+//     run of reference alleles) and loses ~1 % of the entries elsewhere.  max() does not depend on the order the
+//     lanes arrive in and reads and updates are separated by a warp barrier: the same block always gives the same
+//     chains.  (A first version linked equal keys inside a step exactly with __match_any_sync; MATCH.ANY takes time
+//     proportional to the number of distinct keys in the warp and made this phase 4x the cost of everything else.)
 //   * a lookup at position s walks prev[] in its own region, then enters the regions before it through their heads
 //     (all of a previous region precedes s): candidates come nearest first, like zlib's hash chains, at most
 //     `chain` of them; plus the two near distances 4 and 8 bytes that need no table.
@@ -29,9 +33,9 @@
 namespace dnaf {
 
 constexpr int kLStage = 14;            // staged words per span before the block falls back to direct emission
-constexpr uint32_t kLzNone = 0xFFFFu;
+constexpr uint32_t kLzNone = 0xFFFFu;      // prev[] entry / head value of "no earlier position" (heads hold 0 = none, position + 1 otherwise)
 constexpr uint32_t kLzRegion = 4096;   // alleles per region (one warp's 32 spans)
-constexpr uint32_t kLzMaxKey = 10;     // alleles in a key (head tables have 2^(key+1) entries per region)
+constexpr uint32_t kLzMaxKey = 9;      // alleles in a key (head tables have 2^(key+1) 32-bit entries per region)
 constexpr uint32_t kLzMaxDist = 16384; // alleles = 32768 bytes
 
 struct LzCfg {
@@ -46,8 +50,8 @@ struct LzCfg {
 __host__ __device__ inline LzCfg lz_cfg(int level, uint32_t key) {
     LzCfg c;
     c.key = key;
-    c.chain = level <= 4 ? 1u : level == 5 ? 4u : level == 6 ? 16u : level == 7 ? 16u : level == 8 ? 32u : 128u;
-    c.lazy = level >= 7 ? 1u : 0u;
+    c.chain = level <= 4 ? 1u : level == 5 ? 4u : level == 6 ? 8u : level == 7 ? 16u : level == 8 ? 32u : 128u;
+    c.lazy = level >= 6 ? 1u : 0u;
     c.nice = level <= 4 ? 16u : level == 5 ? 32u : level <= 7 ? 64u : 128u;   // zlib: 16, 32, 128, 128, 258, 258 bytes
     return c;
 }
@@ -120,7 +124,7 @@ __host__ __device__ __forceinline__ uint32_t lz_win32(const Mem& mem, uint32_t a
 // The parse is ONE flat loop: every trip compares one 32-allele chunk of one candidate.  All lanes of a warp run the
 // same instructions whatever token or candidate each of them is at -- nested per-token / per-candidate loops made
 // the warp pay for every lane's trip counts in turn (18 of 32 threads active in the first version of this kernel).
-//   stage 0: distance 4 bytes (j = s-2)   stage 1: distance 8 (j = s-4)   stage 2: the key chain of s
+//   stage 0: distance 4 bytes (j = s-2)   stage 1: distance 8 (j = s-4)   stage 3: the key chain of s
 // nice: a match of that many alleles ends the search (zlib's nice_length).
 template <class Mem, class Sink>
 __host__ __device__ __forceinline__ void lz_span_tokens(const Mem& mem, uint32_t a0, int nc, bool first_in_block, bool starts_row,
@@ -151,16 +155,16 @@ __host__ __device__ __forceinline__ void lz_span_tokens(const Mem& mem, uint32_t
             best_k = 0;
             best_da = 0;
             off = 0;
-            stage = s >= 2u ? 0u : 2u;
+            stage = s >= 2u ? 0u : 3u;
             j = s - 2u;
             left = (s + cfg.key <= nall) ? cfg.chain : 0u;
             reg = s / kLzRegion;
             key = (ws0 & kmask) | ((s & 1u) << cfg.key);
             fresh = false;
-            if (stage == 2u) j = left ? mem.prev(s) : kLzNone;
+            if (stage == 3u) j = left ? mem.prev(s) : kLzNone;
         }
         bool done = false;
-        if (stage == 2u) {
+        if (stage == 3u) {
             // resolve the next chain entry: own region first, then the regions before it through their heads
             while (left && j == kLzNone && reg) {
                 --reg;
@@ -192,9 +196,9 @@ __host__ __device__ __forceinline__ void lz_span_tokens(const Mem& mem, uint32_t
                 if (best_k >= limit || best_k >= cfg.nice) done = true;
                 else if (stage == 0u) {
                     if (s >= 4u) { stage = 1u; j = s - 4u; }
-                    else { stage = 2u; j = left ? mem.prev(s) : kLzNone; }
+                    else { stage = 3u; j = left ? mem.prev(s) : kLzNone; }
                 } else if (stage == 1u) {
-                    stage = 2u;
+                    stage = 3u;
                     j = left ? mem.prev(s) : kLzNone;
                 } else {
                     --left;
@@ -249,11 +253,11 @@ struct LzArgs {
 struct LzMemDev {
     const uint32_t* bits;
     const uint16_t* prv;
-    const uint16_t* hd;
+    const uint32_t* hd;      // [region][2^hbits]: last position of the key in the region + 1, 0 = none
     uint32_t hbits;
     __device__ __forceinline__ uint32_t word(uint32_t i) const { return bits[i]; }
     __device__ __forceinline__ uint32_t prev(uint32_t a) const { return prv[a]; }
-    __device__ __forceinline__ uint32_t head(uint32_t reg, uint32_t key) const { return hd[(reg << hbits) + key]; }
+    __device__ __forceinline__ uint32_t head(uint32_t reg, uint32_t key) const { return (hd[(reg << hbits) + key] - 1u) & 0xFFFFu; }
 };
 
 // token-level adapters of the bit sinks (AStageT / AEmit, k_auto.cuh)
@@ -277,7 +281,7 @@ struct LzTokSink {
 
 // dynamic shared memory carve-up
 __host__ __device__ inline uint32_t lz_smem_bytes(uint32_t nthr, uint32_t hbits) {
-    return kLTabWords * 4u + (4u * nthr + 8u) * 4u + (nthr / 32u) * (2u << hbits) + nthr * 256u +
+    return kLTabWords * 4u + (4u * nthr + 8u) * 4u + (nthr / 32u) * (4u << hbits) + nthr * 256u +
            ((uint32_t)(kLStage + 2) * nthr + 24u) * 4u + 16u;
 }
 
@@ -359,37 +363,31 @@ __global__ void __launch_bounds__(256) k_lz(const LzArgs la) {
     }
     const uint32_t key_alleles = __ldg(&tb->key_alleles);
     const uint32_t hbits = key_alleles + 1u;
-    uint16_t* s_head = s_prev + 128u * nthr;
+    uint32_t* s_head = reinterpret_cast<uint32_t*>(s_prev + 128u * nthr);
     {   // heads of this warp's region start empty
-        uint32_t* h32 = reinterpret_cast<uint32_t*>(s_head + ((size_t)wid << hbits));
-        for (uint32_t i = lane; i < (1u << (hbits - 1u)); i += 32u) h32[i] = 0xFFFFFFFFu;
+        uint32_t* h32 = s_head + ((size_t)wid << hbits);
+        for (uint32_t i = lane; i < (1u << hbits); i += 32u) h32[i] = 0u;
     }
     __syncthreads();        // bits complete; also orders the mbarrier's initialisation before the waits
     if (lane == 0 && crc) atomicXor(&s_misc[16], crc);
 
-    // ---- chains of this warp's region, in exact position order: 32 consecutive positions per step.  Positions whose
+    // ---- chains of this warp's region, 32 consecutive positions per step (see the header comment).  Positions whose
     // key runs past the block's end are linked too (their keys hold guard zeros): no lookup can reach them, every
     // candidate lies before a position whose own key fits.
     {
         const uint32_t rbase = kLzRegion * wid;                  // first allele of the region
         const uint32_t rend = min(nall, rbase + kLzRegion);
-        uint16_t* hd = s_head + ((size_t)wid << hbits);
-        const uint32_t kmask = (1u << key_alleles) - 1u, par = (lane & 1u) << key_alleles, below = (1u << lane) - 1u;
+        uint32_t* hd = s_head + ((size_t)wid << hbits);
+        const uint32_t kmask = (1u << key_alleles) - 1u, par = (lane & 1u) << key_alleles;
         uint32_t w0 = s_bits[rbase >> 5];
         for (uint32_t pos = rbase; pos < rend; pos += 32u) {
             const uint32_t w1 = s_bits[(pos >> 5) + 1u];
             const uint32_t key = (__funnelshift_r(w0, w1, lane) & kmask) | par;
             w0 = w1;
-            const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
-            const uint32_t lower = peers & below;
-            uint32_t pv;
-            if (lower) {
-                pv = pos + (31u - (uint32_t)__clz((int)lower));
-            } else {   // the step's first occurrence of this key reads the head and leaves the step's last occurrence there
-                pv = hd[key];
-                hd[key] = (uint16_t)(pos + (31u - (uint32_t)__clz((int)peers)));
-            }
-            s_prev[pos + lane] = (uint16_t)pv;
+            const uint32_t before = hd[key];                     // last occurrence in the steps before this one (+ 1)
+            s_prev[pos + lane] = (uint16_t)(before - 1u);        // 0 -> kLzNone
+            __syncwarp();
+            atomicMax(&hd[key], pos + lane + 1u);
             __syncwarp();
         }
     }

@@ -1,7 +1,7 @@
 #!/bin/bash
 # usage: scripts/gpu_bg.sh <logfile> <timeout> <command...> -- retries gpurun while the pod answers busy (exit 3 / transient)
 log=$1; shift; to=$1; shift
-for i in 1 2 3 4 5 6 7 8; do
+for i in $(seq 1 40); do
   gpurun --timeout $to -- "$@" > $log 2>&1
   if grep -q "status=transient\|retry in a few minutes" $log; then sleep 90; continue; fi
   break
