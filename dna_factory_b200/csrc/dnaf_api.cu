@@ -445,7 +445,7 @@ int dnaf_bgzf_scan(const uint8_t* data, uint64_t n_bytes, uint32_t* csize, uint3
 
 int64_t dnaf_debug_lz_block(double p_minor, int level, const uint32_t* allele_bits, uint32_t n_cells, const uint8_t* prefix,
                             uint32_t prefix_len, int ends_row, uint8_t* out, uint64_t out_cap) {
-    if (level < 4 || level > 9 || !allele_bits || !out || n_cells == 0 || n_cells > 254u * 64u || prefix_len > 64 ||
+    if (level < 3 || level > 9 || !allele_bits || !out || n_cells == 0 || n_cells > 254u * 64u || prefix_len > 64 ||
         (prefix_len && !prefix))
         return DNAF_E_ARG;
     uint64_t hist[256] = {0};

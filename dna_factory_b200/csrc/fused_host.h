@@ -572,8 +572,11 @@ struct LzHist {
     uint64_t nlen[29] = {0};
     uint64_t ndist[30] = {0};
     uint64_t extra = 0;
-    void lit(int id) { nlit[id]++; }
-    void match(int len, int dist) {
+    void emit(bool is_match, int id, int len, int dist) {
+        if (!is_match) {
+            nlit[id]++;
+            return;
+        }
         const int li = len_index(len);
         nlen[li]++;
         uint32_t sym, eb, ev;
@@ -678,12 +681,13 @@ inline double lz_hist_bits(const LzHist& h) {
 // Key length of a MAF bucket: rare minor alleles want long keys (few, long matches), common ones short keys.
 inline uint32_t lz_key_for(double p_minor) {
     const double p = std::min(p_minor, 1.0 - p_minor);
-    return p < 0.12 ? 10u : (p < 0.22 ? 9u : 8u);
+    return std::min<uint32_t>(kLzMaxKey, p < 0.22 ? 9u : 8u);   // the kernel sizes its head tables for kLzMaxKey
 }
 
-inline LzTable make_lz_table(double p_minor, const uint64_t* prefix_hist, int per_block, bool starts_row, int level) {
+// Codes + header of one candidate parse configuration; *total_bits = payload under these codes + the header, per block
+inline LzTable fit_lz_table(double p_minor, const uint64_t* prefix_hist, int per_block, bool starts_row, const LzCfg cfg,
+                            double* total_bits) {
     const int kBlocks = std::max(2, 512 / std::max(1, per_block));
-    const LzCfg cfg = lz_cfg(level, lz_key_for(p_minor));
     const LzHist h = simulate_lz(p_minor, kBlocks, std::max(1, per_block), starts_row, cfg);
     std::vector<uint64_t> f(286, 0), fd(30, 0);
     const uint8_t lit_byte[5] = {'0', '1', '/', '\t', '\n'};
@@ -694,8 +698,9 @@ inline LzTable make_lz_table(double p_minor, const uint64_t* prefix_hist, int pe
     if (prefix_hist)
         for (int c = 0; c < 256; ++c)
             if (prefix_hist[c]) f[c] += std::max<uint64_t>(1, prefix_hist[c]);
-    // every distance a block can need is a multiple of 4 up to 32768: symbols 3 and 5..29
-    for (int i = 3; i < 30; ++i)
+    // every distance a block can need gets a code: multiples of 4 up to 32768 (symbols 3 and 5..29) with the key
+    // chains, only 4 and 8 (symbols 3 and 5) without
+    for (int i = 3; i < (cfg.chain ? 30 : 6); ++i)
         if (i != 4) fd[i] = (h.ndist[i] * scale) / blocks + 1;
     std::vector<uint8_t> ll = huff_lengths(f, 15), dl = huff_lengths(fd, 15);
     std::vector<uint32_t> lc = huff_codes(ll), dc = huff_codes(dl);
@@ -711,11 +716,36 @@ inline LzTable make_lz_table(double p_minor, const uint64_t* prefix_hist, int pe
     t.eob = lc[256];
     for (int i = 0; i < 30; ++i) t.dist_tok[i] = dc[i];
     t.key_alleles = cfg.key;
+    t.chain = cfg.chain;
+    t.lazy = cfg.lazy;
+    t.nice = cfg.nice;
     for (int c = 0; c < 256; ++c) t.pre_lit[c] = lc[c];
     BitString hdr = dynamic_header2(ll, dl);
     t.hdr_bits = hdr.bits;
-    for (size_t i = 0; i < hdr.words.size() && i < 96; ++i) t.hdr[i] = hdr.words[i];
-    if (hdr.words.size() > 96) t.hdr_bits = 0xFFFFFFFFu;
+    for (size_t i = 0; i < hdr.words.size() && i < 94; ++i) t.hdr[i] = hdr.words[i];
+    if (hdr.words.size() > 94) t.hdr_bits = 0xFFFFFFFFu;
+    // payload under the codes just built
+    double bits = (double)h.extra;
+    for (int i = 0; i < 5; ++i) bits += (double)h.nlit[i] * ll[lit_byte[i]];
+    for (int i = 0; i < 29; ++i) bits += (double)h.nlen[i] * ll[257 + i];
+    for (int i = 0; i < 30; ++i) bits += (double)h.ndist[i] * dl[i];
+    *total_bits = bits / (double)blocks + (double)hdr.bits;
+    return t;
+}
+
+// The table of a bucket at a level: the level's own parse, or the near-distances-only parse when that compresses the
+// bucket's rows at least as well (rare minor alleles: few far matches, and a 27-symbol distance code costs header
+// bytes in every block) -- those blocks then skip the chain build altogether.
+inline LzTable make_lz_table(double p_minor, const uint64_t* prefix_hist, int per_block, bool starts_row, int level) {
+    const LzCfg full = lz_cfg(level, lz_key_for(p_minor));
+    double bits_full = 0, bits_near = 0;
+    LzTable t = fit_lz_table(p_minor, prefix_hist, per_block, starts_row, full, &bits_full);
+    if (full.chain) {
+        LzCfg near = full;
+        near.chain = 0;
+        const LzTable tn = fit_lz_table(p_minor, prefix_hist, per_block, starts_row, near, &bits_near);
+        if (tn.hdr_bits != 0xFFFFFFFFu && (t.hdr_bits == 0xFFFFFFFFu || bits_near <= bits_full)) t = tn;
+    }
     return t;
 }
 
@@ -726,8 +756,11 @@ struct LzBitSink {
     const LzTable& t;
     explicit LzBitSink(const LzTable& tt) : t(tt) {}
     void tok(uint32_t v) { bs.put(v & 0xFFFFFFu, (int)(v >> 24)); }
-    void lit(int id) { tok(t.lit[id]); }
-    void match(int len, int dist) {
+    void emit(bool is_match, int id, int len, int dist) {
+        if (!is_match) {
+            tok(t.lit[id]);
+            return;
+        }
         tok(t.len_tok[len]);
         uint32_t sym, eb, ev;
         lz_dist_sym((uint32_t)dist, sym, eb, ev);
@@ -750,7 +783,8 @@ inline std::vector<uint8_t> lz_encode_block_host(const LzTable& t, const uint32_
     }
     const bool starts_row = plen > 0;
     for (uint32_t i = 0; i < plen; ++i) sink.tok(t.pre_lit[prefix[i]]);
-    const LzCfg cfg = lz_cfg(level, t.key_alleles);
+    (void)level;
+    const LzCfg cfg{t.chain, t.lazy, t.key_alleles, t.nice};
     const uint32_t nspans = (ncells + 63u) / 64u;
     for (uint32_t sp = 0; sp < nspans; ++sp) {
         const int nc = (int)std::min(64u, ncells - 64u * sp);

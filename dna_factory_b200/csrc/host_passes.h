@@ -97,7 +97,8 @@ int generate_passes(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t 
     if (rc) return rc;
     if (row_begin > row_end || row_end > c->S) return fail(c, DNAF_E_ARG, "row range out of bounds");
     CU(c, cudaSetDevice(c->dev));
-    // -z 1..3: the byte-4-back parse (k_auto); -z 4..9: LZ77 tiers of growing search depth (k_lz) on autosome rows
+    // -z 1..2: the byte-4-back parse (k_auto); -z 3: distances 4 and 8, -z 4..9: hash-chain LZ77 tiers of growing search
+    // depth (k_lz) on autosome rows
     static const int lz_off = getenv("DNAF_NO_LZ") ? 1 : 0;
     rc = ensure_lz_tables(c, lz_off ? 1 : level);
     if (rc) return rc;
@@ -263,18 +264,15 @@ int generate_passes(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t 
             CU(c, cudaEventRecord(B.ev_auto[0], c->stream));
             const uint32_t ablocks = c->implicit_pass ? c->pass_blocks : (uint32_t)c->fplan.size();
             if (use_lz) {
-                const uint32_t smem = lz_smem_bytes(c->fused_threads, kLzMaxKey + 1u);
+                const LzCfg cfg = lz_cfg(level, kLzMaxKey);
+                const uint32_t smem = lz_smem_bytes(c->fused_threads, kLzMaxKey + 1u, cfg.chain != 0u);
                 if (!c->lz_attr_done) {
-                    CU(c, cudaFuncSetAttribute(k_lz, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lz_smem_bytes(256, kLzMaxKey + 1u)));
+                    CU(c, cudaFuncSetAttribute(k_lz, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lz_smem_bytes(256, kLzMaxKey + 1u, true)));
                     c->lz_attr_done = true;
                 }
                 LzArgs la;
                 la.a = fa;
                 la.tables = c->d_ltables.as<LzTable>();
-                const LzCfg cfg = lz_cfg(level, kLzMaxKey);
-                la.chain = cfg.chain;
-                la.lazy = cfg.lazy;
-                la.nice = cfg.nice;
                 k_lz<<<ablocks, c->fused_threads, smem, c->stream>>>(la);
             } else {
                 k_auto<<<ablocks, c->fused_threads, auto_smem_bytes(c->fused_threads), c->stream>>>(fa);

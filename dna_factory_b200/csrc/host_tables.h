@@ -318,7 +318,7 @@ int ensure_tables(dnaf_ctx* c) {
 // Built lazily at the first dnaf_generate* call that asks for -z >= 4, cached per (bucket, prefix model, level).
 int ensure_lz_tables(dnaf_ctx* c, int level) {
     c->lz_ok = false;
-    if (!c->fused_ok || level < 4 || c->h_seg_crc.empty()) return DNAF_OK;
+    if (!c->fused_ok || level < 3 || c->h_seg_crc.empty()) return DNAF_OK;
     const int nb = (int)c->bucket_p.size();
     const int per_block = (int)std::max<size_t>(1, c->h_seg_cell0.size() > 1
                                                        ? (c->h_seg_cell0[1] - c->h_seg_cell0[0] + 63) / 64 : 1);
@@ -364,7 +364,7 @@ int ensure_lz_tables(dnaf_ctx* c, int level) {
         work();
         for (auto& t : pool) t.join();
         for (size_t i = 0; i < jobs.size(); ++i) {
-            if (res[i].hdr_bits == 0xFFFFFFFFu) return DNAF_OK;   // header too long: the call stays on k_auto
+            if (res[i].hdr_bits == 0xFFFFFFFFu || res[i].key_alleles > kLzMaxKey) return DNAF_OK;   // header too long: the call stays on k_auto
             c->ltable_cache.emplace(jobs[i].key, res[i]);
         }
     }

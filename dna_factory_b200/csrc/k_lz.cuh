@@ -45,12 +45,13 @@ struct LzCfg {
     uint32_t nice;    // alleles: a match this long ends the search
 };
 
-// -z level -> parse parameters (zlib's own ladder: max_chain 16 / 32 / 128 / 256 / 1024 / 4096 for 4 .. 9, quartered
-// here because every chain entry is already a >= 2*key byte match)
+// -z level -> parse parameters.  3: the two near distances only (no tables are built); 4..9: zlib's own ladder shape
+// (its max_chain is 16 / 32 / 128 / 256 / 1024 / 4096 there; shorter here because every chain entry is already a
+// >= 2*key byte match), lazy evaluation from 6 on.
 __host__ __device__ inline LzCfg lz_cfg(int level, uint32_t key) {
     LzCfg c;
     c.key = key;
-    c.chain = level <= 4 ? 1u : level == 5 ? 4u : level == 6 ? 8u : level == 7 ? 16u : level == 8 ? 32u : 128u;
+    c.chain = level <= 3 ? 0u : level == 4 ? 1u : level == 5 ? 4u : level == 6 ? 16u : level == 7 ? 32u : level == 8 ? 64u : 128u;
     c.lazy = level >= 6 ? 1u : 0u;
     c.nice = level <= 4 ? 16u : level == 5 ? 32u : level <= 7 ? 64u : 128u;   // zlib: 16, 32, 128, 128, 258, 258 bytes
     return c;
@@ -64,13 +65,15 @@ struct LzTable {
     uint32_t eob;
     uint32_t hdr_bits;
     uint32_t dist_tok[32];   // [distance symbol]: code | bits << 24
-    uint32_t key_alleles;
-    uint32_t pad;
-    uint32_t hdr[96];        // serialized dynamic-block header
+    uint32_t key_alleles;    // the parse parameters this table's codes were fitted to (LzCfg): a bucket whose rows
+    uint32_t chain;          // compress no better with the key chains (rare minor alleles: the dynamic-block header
+    uint32_t lazy;           // of a code with 27 distance symbols outweighs what far matches save) keeps chain = 0
+    uint32_t nice;           // and its blocks skip the chain build
+    uint32_t hdr[94];        // serialized dynamic-block header
     // ----
     uint32_t pre_lit[256];   // literal codes of prefix bytes
 };
-constexpr uint32_t kLTabWords = 260 + 8 + 2 + 32 + 2 + 96;   // 400 words = 100 x 16 bytes
+constexpr uint32_t kLTabWords = 260 + 8 + 2 + 32 + 4 + 94;   // 400 words = 100 x 16 bytes
 static_assert(kLTabWords % 4 == 0 && sizeof(LzTable) % 16 == 0, "LzTable must copy in 16-byte units");
 
 __host__ __device__ __forceinline__ uint32_t lz_fsr(uint32_t lo, uint32_t hi, uint32_t sh) {
@@ -81,14 +84,6 @@ __host__ __device__ __forceinline__ uint32_t lz_fsr(uint32_t lo, uint32_t hi, ui
     return sh ? (lo >> sh) | (hi << (32u - sh)) : lo;
 #endif
 }
-__host__ __device__ __forceinline__ uint32_t lz_ctz64(uint64_t x) {
-#ifdef __CUDA_ARCH__
-    return (uint32_t)__ffsll((long long)x) - 1u;
-#else
-    return (uint32_t)__builtin_ctzll(x);
-#endif
-}
-
 // distance (bytes, 1..32768) -> deflate distance symbol, number of extra bits, extra value
 __host__ __device__ __forceinline__ void lz_dist_sym(uint32_t d, uint32_t& sym, uint32_t& eb, uint32_t& ev) {
     if (d <= 4u) { sym = d - 1u; eb = 0; ev = 0; return; }
@@ -114,17 +109,41 @@ __host__ __device__ __forceinline__ void lz_dist_sym(uint32_t d, uint32_t& sym, 
 //   that last separator when it is not the span's; >= 3 bytes -> match, else one literal byte.
 //   ['\n' if the span ends the row] [EOB if it ends the block]
 // Mem: word(i) = allele bits 32i .. 32i+31 of the block (zero past the end), prev(a), head(region, key).
-// Sink: lit(id), match(len bytes, dist bytes), eob().
+// Sink: emit(is_match, literal id, len bytes, dist bytes), eob().
 template <class Mem>
 __host__ __device__ __forceinline__ uint32_t lz_win32(const Mem& mem, uint32_t a) {
     const uint32_t w = a >> 5;
     return lz_fsr(mem.word(w), mem.word(w + 1u), a & 31u);
 }
 
-// The parse is ONE flat loop: every trip compares one 32-allele chunk of one candidate.  All lanes of a warp run the
-// same instructions whatever token or candidate each of them is at -- nested per-token / per-candidate loops made
-// the warp pay for every lane's trip counts in turn (18 of 32 threads active in the first version of this kernel).
-//   stage 0: distance 4 bytes (j = s-2)   stage 1: distance 8 (j = s-4)   stage 3: the key chain of s
+__host__ __device__ __forceinline__ uint32_t lz_ctz32(uint32_t x) {   // x != 0
+#ifdef __CUDA_ARCH__
+    return (uint32_t)__ffs((int)x) - 1u;
+#else
+    return (uint32_t)__builtin_ctz(x);
+#endif
+}
+
+// alleles from s + 32 on that equal those from j + 32 on, given that the first 32 are equal: 32 + ... (<= limit)
+template <class Mem>
+__host__ __device__ __forceinline__ uint32_t lz_extend(const Mem& mem, uint32_t s, uint32_t j, uint32_t limit) {
+    uint32_t off = 32u;
+    for (;;) {
+        const uint32_t x = lz_win32(mem, s + off) ^ lz_win32(mem, j + off);
+        const uint32_t room = limit - off;
+        uint32_t c = x ? lz_ctz32(x) : 32u;
+        c = c < room ? c : room;
+        if (c == 32u && room > 32u) off += 32u;
+        else return off + c;
+    }
+}
+
+// One trip of the loop = one LOOKUP (at byte p, for allele s) and the token it ends in.  The lanes of a warp stay
+// together at that granularity: set-up and the two near distances (4 and 8 bytes: j = s-2, s-4, compared from the
+// same three words that hold s's own window), then the key chain of s nearest first (own region, then the regions
+// before it through their heads), then ONE emit.  (Two earlier shapes were measured: nested per-token loops left
+// 18 of 32 threads active, a fully flat one-candidate-per-trip state machine 13 of 32 -- the lanes of a trip were in
+// different states and the warp ran every state's code.)
 // nice: a match of that many alleles ends the search (zlib's nice_length).
 template <class Mem, class Sink>
 __host__ __device__ __forceinline__ void lz_span_tokens(const Mem& mem, uint32_t a0, int nc, bool first_in_block, bool starts_row,
@@ -133,121 +152,98 @@ __host__ __device__ __forceinline__ void lz_span_tokens(const Mem& mem, uint32_t
     auto bit = [&](uint32_t a) { return (int)((mem.word(a >> 5) >> (a & 31u)) & 1u); };
     int p = 2 * (int)a0 - 1;                        // next byte to emit (block coordinates)
     if (first_in_block) {
-        if (!starts_row) sink.lit(kLitTab);
-        sink.lit(bit(a0));
-        sink.lit(kLitSlash);
-        sink.lit(bit(a0 + 1u));
+        if (!starts_row) sink.emit(false, kLitTab, 0, 0);
+        sink.emit(false, bit(a0), 0, 0);
+        sink.emit(false, kLitSlash, 0, 0);
+        sink.emit(false, bit(a0 + 1u), 0, 0);
         p = 2 * (int)a0 + 3;
     }
     const int pend = 2 * (int)aend - 1;             // one past the span's last byte
     const uint32_t kmask = (1u << cfg.key) - 1u;
-    // lookup state
-    uint32_t s = 0, limit = 0, ws0 = 0, stage = 0, j = 0, off = 0, left = 0, reg = 0, key = 0;
-    uint32_t best_k = 0, best_da = 0;
     // lazy evaluation: the finished lookup at the byte before (held while the next allele is examined)
     uint32_t held_len = 0, held_da = 0;
-    bool held = false, fresh = true;
+    bool held = false;
     while (p < pend) {
-        if (fresh) {   // set up the lookup at byte p
-            s = (uint32_t)(p + 1) >> 1;
-            limit = aend - s;                        // s < aend here: the span's last byte is an allele
-            ws0 = lz_win32(mem, s);
-            best_k = 0;
-            best_da = 0;
-            off = 0;
-            stage = s >= 2u ? 0u : 3u;
-            j = s - 2u;
-            left = (s + cfg.key <= nall) ? cfg.chain : 0u;
-            reg = s / kLzRegion;
-            key = (ws0 & kmask) | ((s & 1u) << cfg.key);
-            fresh = false;
-            if (stage == 3u) j = left ? mem.prev(s) : kLzNone;
+        const uint32_t s = (uint32_t)(p + 1) >> 1;
+        const uint32_t limit = aend - s;             // s < aend here: the span's last byte is an allele
+        // alleles lo .. lo+63 with lo = s - 4 (s >= 4 everywhere but in the first cells of a block)
+        const uint32_t lo = s >= 4u ? s - 4u : 0u, sh0 = s - lo;
+        const uint32_t w = lo >> 5, sh = lo & 31u;
+        const uint32_t x0 = mem.word(w), x1 = mem.word(w + 1u), x2 = mem.word(w + 2u);
+        const uint32_t v0 = lz_fsr(x0, x1, sh), v1 = lz_fsr(x1, x2, sh);
+        const uint32_t ws0 = lz_fsr(v0, v1, sh0);
+        const uint32_t room = limit < 32u ? limit : 32u;
+        uint32_t k1 = 0, k2 = 0;
+        if (s >= 2u) {
+            const uint32_t d1 = ws0 ^ lz_fsr(v0, v1, sh0 - 2u);
+            k1 = d1 ? lz_ctz32(d1) : 32u;
+            k1 = k1 < room ? k1 : room;
         }
-        bool done = false;
-        if (stage == 3u) {
-            // resolve the next chain entry: own region first, then the regions before it through their heads
-            while (left && j == kLzNone && reg) {
-                --reg;
-                j = mem.head(reg, key);
-            }
-            if (!left || j == kLzNone || s - j > kLzMaxDist) done = true;
+        if (s >= 4u) {
+            const uint32_t d2 = ws0 ^ v0;
+            k2 = d2 ? lz_ctz32(d2) : 32u;
+            k2 = k2 < room ? k2 : room;
         }
-        if (!done) {
-            // one 32-allele chunk of candidate j
-            const uint32_t a = off ? lz_win32(mem, s + off) : ws0;
-            const uint32_t x = a ^ lz_win32(mem, j + off);
-            const uint32_t room = limit - off;
-#ifdef __CUDA_ARCH__
-            uint32_t c = x ? (uint32_t)__ffs((int)x) - 1u : 32u;
-#else
-            uint32_t c = x ? (uint32_t)__builtin_ctz(x) : 32u;
-#endif
-            c = c < room ? c : room;
-            if (c == 32u && room > 32u) {
-                off += 32u;                          // same candidate, next chunk
-            } else {
-                const uint32_t k = off + c;
+        uint32_t best_k = k2 > k1 ? k2 : k1;
+        uint32_t best_da = k2 > k1 ? 4u : 2u;
+        if (best_k == 32u && limit > 32u) best_k = lz_extend(mem, s, s - best_da, limit);   // the nearer one goes on
+        if (cfg.chain && best_k < limit && best_k < cfg.nice && s + cfg.key <= nall) {
+            const uint32_t key = (ws0 & kmask) | ((s & 1u) << cfg.key);
+            uint32_t reg = s / kLzRegion;
+            uint32_t j = mem.prev(s);
+            for (uint32_t n = 0; n < cfg.chain; ++n) {
+                while (j == kLzNone && reg) {
+                    --reg;
+                    j = mem.head(reg, key);
+                }
+                if (j == kLzNone || s - j > kLzMaxDist) break;
+                const uint32_t x = ws0 ^ lz_win32(mem, j);
+                uint32_t k = x ? lz_ctz32(x) : 32u;
+                k = k < room ? k : room;
+                if (k == 32u && limit > 32u) k = lz_extend(mem, s, j, limit);
                 if (k > best_k) {
                     best_k = k;
                     best_da = s - j;
+                    if (k >= limit || k >= cfg.nice) break;
                 }
-                off = 0;
-                // next candidate
-                if (best_k >= limit || best_k >= cfg.nice) done = true;
-                else if (stage == 0u) {
-                    if (s >= 4u) { stage = 1u; j = s - 4u; }
-                    else { stage = 3u; j = left ? mem.prev(s) : kLzNone; }
-                } else if (stage == 1u) {
-                    stage = 3u;
-                    j = left ? mem.prev(s) : kLzNone;
-                } else {
-                    --left;
-                    j = mem.prev(j);
-                }
+                j = mem.prev(j);
             }
         }
-        if (done) {
-            const uint32_t odd = (uint32_t)p & 1u;
-            // bytes p .. 2(s+k)-1, minus the separator after the span's last allele
-            const int len = 2 * (int)(s + best_k) - p - (s + best_k == aend ? 1 : 0);
-            if (held) {
-                // p is the byte after the held lookup's: take the literal + this match if that is longer
-                held = false;
-                if (len > (int)held_len + 1) {
-                    sink.lit(bit(s - 1u));
-                    sink.match(len, 2 * (int)best_da);
-                    p += len;
-                } else {
-                    sink.match((int)held_len, 2 * (int)held_da);
-                    p += (int)held_len - 1;
-                }
-            } else if (len >= 3) {
-                if (cfg.lazy && !odd && s + 1u < aend && s + best_k < aend && best_k < cfg.nice) {
-                    held = true;                     // would a literal now buy a longer match from the next byte on?
-                    held_len = (uint32_t)len;
-                    held_da = best_da;
-                    p += 1;
-                } else {
-                    sink.match(len, 2 * (int)best_da);
-                    p += len;
-                }
+        const uint32_t odd = (uint32_t)p & 1u;
+        // bytes p .. 2(s+k)-1, minus the separator after the span's last allele
+        int len = 2 * (int)(s + best_k) - p - (s + best_k == aend ? 1 : 0);
+        if (held) {
+            // p is the byte after the held lookup's: take the literal + this match if that is longer
+            held = false;
+            if (len > (int)held_len + 1) {
+                sink.emit(false, bit(s - 1u), 0, 0);
             } else {
-                if (odd) sink.lit((s & 1u) ? kLitSlash : kLitTab);   // separator before allele s
-                else sink.lit(bit(s));
-                p += 1;
+                len = (int)held_len;
+                best_da = held_da;
+                p -= 1;
             }
-            fresh = true;
+            sink.emit(true, 0, len, 2 * (int)best_da);
+            p += len;
+        } else if (len >= 3 && cfg.lazy && !odd && s + 1u < aend && s + best_k < aend && best_k < cfg.nice) {
+            held = true;                             // would a literal now buy a longer match from the next byte on?
+            held_len = (uint32_t)len;
+            held_da = best_da;
+            p += 1;
+        } else {
+            const bool is_match = len >= 3;
+            const int id = odd ? ((s & 1u) ? kLitSlash : kLitTab) : (int)((ws0 & 1u));   // separator before allele s / allele s
+            sink.emit(is_match, id, len, 2 * (int)best_da);
+            p += is_match ? len : 1;
         }
     }
-    if (ends_row) sink.lit(kLitNl);
+    if (ends_row) sink.emit(false, kLitNl, 0, 0);
     if (ends_block) sink.eob();
 }
 
 #ifdef __CUDACC__
 struct LzArgs {
     AutoArgs a;
-    const LzTable* tables;   // [2 * bucket + (segment 0 ? 0 : 1)]
-    uint32_t chain, lazy, nice;
+    const LzTable* tables;   // [2 * bucket + (segment 0 ? 0 : 1)]; parse parameters come from the table
 };
 
 struct LzMemDev {
@@ -260,7 +256,7 @@ struct LzMemDev {
     __device__ __forceinline__ uint32_t head(uint32_t reg, uint32_t key) const { return (hd[(reg << hbits) + key] - 1u) & 0xFFFFu; }
 };
 
-// token-level adapters of the bit sinks (AStageT / AEmit, k_auto.cuh)
+// token-level adapter of the bit sinks (AStageT / AEmit, k_auto.cuh): literal or match through ONE append
 template <class Bits>
 struct LzTokSink {
     Bits& b;
@@ -268,21 +264,26 @@ struct LzTokSink {
     const uint32_t* lits;
     const uint32_t* dist_tok;
     uint32_t eob_tok;
-    __device__ __forceinline__ void lit(int id) { const uint32_t t = lits[id]; b.put64(t & 0xFFFFFFu, 0u, t >> 24); }
-    __device__ __forceinline__ void match(int len, int dist) {
-        uint32_t sym, eb, ev;
-        lz_dist_sym((uint32_t)dist, sym, eb, ev);
-        const uint32_t dt = dist_tok[sym];
-        const uint32_t dn = dt >> 24;
-        b.put_tok_code(len_tok[len], (dt & 0xFFFFFFu) | (ev << dn), 0u, dn + eb);   // <= 20 + 28 bits
+    __device__ __forceinline__ void emit(bool is_match, int id, int len, int dist) {
+        const uint32_t t1 = is_match ? len_tok[len] : lits[id];
+        uint32_t c = 0, nb = 0;
+        if (is_match) {
+            uint32_t sym, eb, ev;
+            lz_dist_sym((uint32_t)dist, sym, eb, ev);
+            const uint32_t dt = dist_tok[sym];
+            const uint32_t dn = dt >> 24;
+            c = (dt & 0xFFFFFFu) | (ev << dn);
+            nb = dn + eb;
+        }
+        b.put_tok_code(t1, c, 0u, nb);   // <= 20 + 28 bits
     }
     __device__ __forceinline__ void eob() { b.put64(eob_tok & 0xFFFFFFu, 0u, eob_tok >> 24); }
 };
 
 // dynamic shared memory carve-up
-__host__ __device__ inline uint32_t lz_smem_bytes(uint32_t nthr, uint32_t hbits) {
-    return kLTabWords * 4u + (4u * nthr + 8u) * 4u + (nthr / 32u) * (4u << hbits) + nthr * 256u +
-           ((uint32_t)(kLStage + 2) * nthr + 24u) * 4u + 16u;
+__host__ __device__ inline uint32_t lz_smem_bytes(uint32_t nthr, uint32_t hbits, bool with_chains) {
+    return kLTabWords * 4u + (4u * nthr + 8u) * 4u + ((uint32_t)(kLStage + 2) * nthr + 24u) * 4u + 16u +
+           (with_chains ? (nthr / 32u) * (4u << hbits) + nthr * 256u : 0u);   // heads + prev[] come last
 }
 
 __global__ void __launch_bounds__(256) k_lz(const LzArgs la) {
@@ -297,7 +298,7 @@ __global__ void __launch_bounds__(256) k_lz(const LzArgs la) {
     const uint32_t* s_len = s_tab;
     const uint32_t* s_lits = s_tab + 260;
     const uint32_t* s_dist = s_tab + 270;
-    const uint32_t* s_hdr = s_tab + 304;
+    const uint32_t* s_hdr = s_tab + 306;
 
     FusedDesc d;
     if (a.desc) {
@@ -361,10 +362,10 @@ __global__ void __launch_bounds__(256) k_lz(const LzArgs la) {
         *reinterpret_cast<uint4*>(s_bits + 4u * tid) = make_uint4(mm[0], mm[1], mm[2], mm[3]);
         if (tid < 8) s_bits[4u * nthr + tid] = 0u;
     }
-    const uint32_t key_alleles = __ldg(&tb->key_alleles);
+    const uint32_t key_alleles = __ldg(&tb->key_alleles), chain = __ldg(&tb->chain);
     const uint32_t hbits = key_alleles + 1u;
     uint32_t* s_head = reinterpret_cast<uint32_t*>(s_prev + 128u * nthr);
-    {   // heads of this warp's region start empty
+    if (chain) {   // heads of this warp's region start empty
         uint32_t* h32 = s_head + ((size_t)wid << hbits);
         for (uint32_t i = lane; i < (1u << hbits); i += 32u) h32[i] = 0u;
     }
@@ -374,7 +375,7 @@ __global__ void __launch_bounds__(256) k_lz(const LzArgs la) {
     // ---- chains of this warp's region, 32 consecutive positions per step (see the header comment).  Positions whose
     // key runs past the block's end are linked too (their keys hold guard zeros): no lookup can reach them, every
     // candidate lies before a position whose own key fits.
-    {
+    if (chain) {
         const uint32_t rbase = kLzRegion * wid;                  // first allele of the region
         const uint32_t rend = min(nall, rbase + kLzRegion);
         uint32_t* hd = s_head + ((size_t)wid << hbits);
@@ -399,7 +400,7 @@ __global__ void __launch_bounds__(256) k_lz(const LzArgs la) {
     const bool worker = nc > 0;
     const bool p_last = worker && 64u * tid + (uint32_t)nc == d.ncells;
     const bool p_end = ends_row && p_last;
-    const LzCfg cfg{la.chain, la.lazy, key_alleles, la.nice};
+    const LzCfg cfg{chain, s_tab[304], key_alleles, s_tab[305]};
     const LzMemDev mem{s_bits, s_prev, s_head, hbits};
     AStageT<kLStage> st{s_stage + tid, nthr, 0u, 0u, 0u};
     if (worker) {

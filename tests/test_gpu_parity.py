@@ -128,14 +128,14 @@ def test_fused_kernel_vs_oracle_and_generic(native, n, s, seed):
 @pytest.mark.parametrize("n,s,seed", [(4096, 10, 51), (4160, 8, 52), (16256, 5, 53), (16257, 5, 54), (20000, 24, 55),
                                       (33000, 6, 56), (100003, 4, 57)])
 def test_lz_tiers_decompress_to_the_oracle_rows(native, n, s, seed):
-    """-z 4..9 run the LZ77 kernel k_lz on autosome rows (pop_factory.py:403 hands -z to the writer): every level must
+    """-z 3..9 run the LZ77 kernel k_lz on autosome rows (pop_factory.py:403 hands -z to the writer): every level must
     decompress to the oracle's rows, be deterministic (two runs, same bytes), and a deeper tier must not be larger."""
     from oracle import oracle
     case = synth_case(n, s, seed=seed, chroms=['1', '2', '1', '7', 'X', '22', 'Y'], n_del=40)
     want, _ = oracle.rows(case.samples, case.snps, case.seed, 0, n_threads=4)
     eng = _engine(native, case, chunk=8 << 20)
     sizes = {}
-    for level in (3, 4, 5, 6, 7, 8, 9):
+    for level in (2, 3, 4, 5, 6, 7, 8, 9):
         blob, st = eng.generate(0, s, case.seed, level=level)
         text, blocks, _ = oracle.bgzf_decompress(blob)
         assert text == want, "level %d" % level
@@ -144,13 +144,13 @@ def test_lz_tiers_decompress_to_the_oracle_rows(native, n, s, seed):
         assert again == blob, "level %d is not deterministic" % level
         sizes[level] = len(blob)
     # a handful of rows: allow 1.5 % noise between neighbouring tiers (the large-sample check is bench.py's level_sweep)
-    assert all(sizes[b] <= 1.015 * sizes[a] for a, b in zip((3, 4, 5, 6, 7, 8), (4, 5, 6, 7, 8, 9))), sizes
-    assert sizes[9] <= sizes[4] <= sizes[3], sizes
+    assert all(sizes[b] <= 1.015 * sizes[a] for a, b in zip((2, 3, 4, 5, 6, 7, 8), (3, 4, 5, 6, 7, 8, 9))), sizes
+    assert sizes[9] <= sizes[4] <= sizes[2], sizes
     if s >= 20:
-        assert sizes[6] < 0.85 * sizes[3], sizes
+        assert sizes[6] < 0.85 * sizes[2], sizes
 
 
-@pytest.mark.parametrize("level", [4, 6, 9])
+@pytest.mark.parametrize("level", [3, 4, 6, 9])
 def test_lz_tiers_dense_overrides(native, level):
     """The dense forced-minor patterns of test_auto_kernel_dense_overrides_on_rare_rows through k_lz: spans that
     overflow their staging words re-emit straight into the block, every symbol has a code."""

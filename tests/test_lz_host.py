@@ -1,4 +1,4 @@
-"""CPU tests of the LZ tiers' (-z 4..9) span grammar, static code tables and dynamic-block header: the host twin of
+"""CPU tests of the LZ tiers' (-z 3..9) span grammar, static code tables and dynamic-block header: the host twin of
 k_lz (same lz_span_tokens function, same table builder) encodes synthetic autosome segments, zlib inflates them.
 No GPU involved; the device path is checked against the oracle in tests/test_gpu_parity.py."""
 import zlib
@@ -27,7 +27,7 @@ def _segment(n_cells, p, seed, first_byte_tab, ends_row, forced=None):
     return bits, (b"\t" if first_byte_tab else b"") + body
 
 
-@pytest.mark.parametrize("level", [4, 5, 6, 7, 8, 9])
+@pytest.mark.parametrize("level", [3, 4, 5, 6, 7, 8, 9])
 @pytest.mark.parametrize("p", [0.005, 0.03, 0.11, 0.2, 0.35, 0.495])
 def test_lz_block_inflates_to_the_text(level, p):
     for n_cells, with_prefix, ends_row, seed in ((10048, True, False, 1), (9952, False, True, 2), (777, True, True, 3),
@@ -44,7 +44,7 @@ def test_lz_block_handles_patterns_the_tables_never_expect():
     n_cells = 9000
     forced = np.arange(4000, 9000)           # thousands of 1/1 cells in a row on a MAF 0.005 table
     bits, body = _segment(n_cells, 0.005, 7, True, False, forced)
-    for level in (4, 6, 9):
+    for level in (3, 4, 6, 9):
         enc = _native.debug_lz_block(0.005, level, bits, n_cells, b"", False)
         assert zlib.decompress(enc, -15) == body
 
@@ -52,10 +52,10 @@ def test_lz_block_handles_patterns_the_tables_never_expect():
 def test_lz_levels_are_monotone_on_the_reference_maf_mix():
     """Deeper tiers must not compress worse (pop_factory.py:403 hands -z to the writer; BASELINE config 5)."""
     sizes = {}
-    for level in (4, 5, 6, 7, 8, 9):
+    for level in (3, 4, 5, 6, 7, 8, 9):
         tot = 0
         for i, p in enumerate((0.01, 0.03, 0.08, 0.15, 0.3, 0.45)):
             bits, body = _segment(10048, p, 40 + i, True, False)
             tot += len(_native.debug_lz_block(p, level, bits, 10048, b"", False))
         sizes[level] = tot
-    assert all(sizes[a] >= sizes[b] for a, b in zip((4, 5, 6, 7, 8), (5, 6, 7, 8, 9))), sizes
+    assert all(sizes[a] >= sizes[b] for a, b in zip((3, 4, 5, 6, 7, 8), (4, 5, 6, 7, 8, 9))), sizes
