@@ -162,20 +162,25 @@ def cpu_reference_run(steps, warmup, budget_s=20.0):
 
 
 def _inflate_bgzf(blob):
-    """Decompressed bytes of a BGZF stream without EOF block (plain zlib, member by member)."""
-    import zlib
-    out, data = [], memoryview(blob)
-    while len(data):
-        d = zlib.decompressobj(31)
-        out.append(d.decompress(data))
-        data = data[len(data) - len(d.unused_data):]
-    return b"".join(out)
+    """Decompressed bytes of a BGZF stream without EOF block (zlib, block by block, CRC32 / ISIZE checked)."""
+    from dna_factory_b200 import allele_stats
+    return allele_stats.inflate_bgzf(blob)
+
+
+def _lap(what, t0=[time.perf_counter()]):
+    """Phase timing on stderr (the JSON line on stdout stays alone)."""
+    now = time.perf_counter()
+    print("[bench] %-34s +%.1f s" % (what, now - t0[0]), file=sys.stderr, flush=True)
+    t0[0] = now
 
 
 def run_extras(eng, torch, stream, R, n_steps_total, arrays, orow, osamp, row_base, local_rank):
-    """Extra keys of the 1-GPU line (module docstring).  `eng` still holds the whole resident table."""
+    """Extra keys of the 1-GPU line (module docstring)."""
     from dna_factory_b200 import _native, allele_stats
     out = {}
+    eng.set_snps(**arrays)          # the e2e pass left one step's slice in the context: the whole table again
+    eng.set_overrides(orow, osamp)
+    eng.set_row_base(row_base)
     n_rows = 2 * n_steps_total * R
     n = N_CASES + N_CONTROLS
     # ---- value_sustained: back-to-back device-only calls over the whole resident table for >= 1 s (the timed `value`
@@ -192,6 +197,7 @@ def run_extras(eng, torch, stream, R, n_steps_total, arrays, orow, osamp, row_ba
     torch.cuda.synchronize()
     out["value_sustained"] = {"value": calls / (ev0.elapsed_time(ev1) * 1e-3), "unit": "calls/s", "seconds": ev0.elapsed_time(ev1) * 1e-3,
                               "what": "dnaf_generate_device over %d resident rows x %d samples, repeated back to back, -z %d" % (n_rows, n, LEVEL)}
+    _lap("value_sustained")
     # ---- level_sweep: BASELINE config 5 (-z 1..9 on 20 000 samples), one window of rows per level
     sweep_rows = min(n_rows, 4 * R)
     out_buf = torch.empty(int(eng.plan(0, sweep_rows)[1]) + (1 << 20), dtype=torch.uint8, pin_memory=True).numpy()
@@ -210,13 +216,16 @@ def run_extras(eng, torch, stream, R, n_steps_total, arrays, orow, osamp, row_ba
                           "e2e": st2["calls"] / dt, "bgzf_bytes_per_call": st["bgzf_bytes"] / st["calls"]}
     out["level_sweep"] = {"rows": sweep_rows, "samples": n, "note": "value: device only; e2e: one call, BGZF bytes into pinned host memory "
                           "(SNP table resident)", "levels": sweep}
+    _lap("level_sweep")
     # ---- the drop-in CLI writing a real population.vcf.gz (C2 shape, SNP axis cut to 65536 rows)
     try:
         out["cli_to_file"] = cli_to_file(65536)
     except Exception as e:   # noqa: a full disk or a missing tmp dir must not cost the bench line
         out["cli_to_file"] = {"error": "%s: %s" % (type(e).__name__, e)}
+    _lap("cli_to_file")
     # ---- allele-frequency chi-square of the draws (north_star), >= 1e8 calls
     out["allele_chi_square"] = allele_stats.chi_square_report(level=LEVEL, device=local_rank)
+    _lap("allele_chi_square")
     return out
 
 
@@ -347,6 +356,7 @@ def main():
     def sum_over_ranks(x):
         return partition.reduce_sum(x, dist if world > 1 else None, "cuda")
 
+    _lap("population + context ready")
     # ------------------------------------------------------------------ device-resident pass (`value`)
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -410,6 +420,7 @@ def main():
                 "stage_ms_per_step": {k.replace("ms_", ""): v / len(stats) for k, v in stage_ms.items()},
                 "pipeline_frac": (text_bytes / (sum(s["ms_total"] for s in stats) * 1e-3) / 1e9) / peak}
 
+    _lap("value pass")
     # ------------------------------------------------------------------ end-to-end pass (`e2e`)
     # host buffers in, host buffer out: per step the step's SNP metadata goes H2D, the BGZF bytes come D2H
     # page-locked output buffer: the library DMAs straight into it; smaller passes so that the copy of one pass
@@ -477,6 +488,7 @@ def main():
     launches += 0  # e2e launches are outside the `value` region
 
 
+    _lap("e2e pass")
     # ------------------------------------------------------------------ multi-GPU parity (N > 1)
     # Every rank regenerates nothing on trust: it inflates a window at the START of its own SNP range (produced with
     # its own row_base) and publishes (text bytes, blocks, CRC32 of the text); rank 0 recomputes every rank's window
@@ -553,6 +565,7 @@ def main():
                         "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                 "compression_ratio": text_bytes / max(1, bgzf_bytes), "text_gb_per_s": text_bytes / (ms * 1e-3) / 1e9}
+        _lap("cpu baselines")
         if cpu_port is not None:
             line["cpu_baseline_port"] = cpu_port
             line["cpu_baseline_python"] = cpu if cpu is not cpu_port else None
