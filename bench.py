@@ -450,13 +450,15 @@ def main():
 
     batches = [step_arrays(k) for k in range(n_steps_total)]
 
+    e2e_level = [args.level]
+
     def e2e_step(j, b):
         a, o_r, o_s, lo = b
         e = engines[j]
         e.set_snps(**a)
         e.set_overrides(o_r, o_s)
         e.set_row_base(row_base + lo)
-        return e.generate_into(0, R, PHILOX_SEED, outs[j], level=args.level)
+        return e.generate_into(0, R, PHILOX_SEED, outs[j], level=e2e_level[0])
 
     def run_steps(ks):
         """Steps ks, dealt round-robin to the contexts; every context runs its steps in order on its own thread."""
@@ -486,6 +488,24 @@ def main():
                        batches[warmup:]]))
     d2h = int(np.mean([s["bgzf_bytes"] for s in e2e_stats]))
     launches += 0  # e2e launches are outside the `value` region
+    # the same end-to-end steps at the reference's default -z 6 and at -z 4: past one GPU the host's PCIe fabric bounds
+    # the rate, so fewer compressed bytes per call are worth more than kernel time (BASELINE config 5 at 1/2/4/8 GPUs)
+    e2e_by_level = {str(args.level): e2e_calls / e2e_s}
+    if not args.no_extras:
+        for lv in (4, 6):
+            if lv == args.level:
+                continue
+            e2e_level[0] = lv
+            ks = list(range(warmup, n_steps_total))[:6]
+            run_steps(ks[:2] * n_ctx)                       # tables of the tier, warm-up
+            barrier()
+            t1 = time.perf_counter()
+            st_l = run_steps(ks)
+            torch.cuda.synchronize()
+            dt = max_over_ranks(time.perf_counter() - t1)
+            barrier()
+            e2e_by_level[str(lv)] = sum_over_ranks(sum(x["calls"] for x in st_l)) / dt
+        e2e_level[0] = args.level
 
 
     _lap("e2e pass")
@@ -570,6 +590,7 @@ def main():
             line["cpu_baseline_port"] = cpu_port
             line["cpu_baseline_python"] = cpu if cpu is not cpu_port else None
             line["cpu_baseline_c1_full"] = cpu_c1
+        line["e2e_by_level"] = e2e_by_level
         if multi_gpu_parity is not None:
             line["multi_gpu_parity"] = multi_gpu_parity
         line.update(extras)

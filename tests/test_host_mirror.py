@@ -212,3 +212,120 @@ def test_native_formatters_match_the_python_ones(tmp_path):
     got = gzip.open(tmp_path / "a.gz", "rb").read()
     assert got == gzip.open(tmp_path / "b.gz", "rb").read()
     assert got.decode().splitlines() == [str(s) for s in tab.to_snps()]
+
+
+def test_offset_replay_host_files_match_reference(tmp_path, monkeypatch):
+    """The README's multi-run recipe (README.md:88-94, pop_factory.py:350-351,378): `--offset 300` replayed from
+    snps.json.gz / deleterious.json -- population.fam, pop_deleterious.txt and the VCF header's sample ids byte for
+    byte against the pinned reference run (tests/golden/cli_offset; the rows need the GPU: test_gpu_cli.py)."""
+    from dna_factory_b200 import pop_factory
+    gold = os.path.join(GOLDEN, "cli_offset")
+    src = os.path.join(GOLDEN, "cli_small")
+    meta = json.load(open(os.path.join(gold, "meta.json")))
+
+    class FixedDatetime(pop_factory.datetime):
+        @classmethod
+        def now(cls, tz=None):
+            return cls(2026, 1, 1, 12, 34, 56)
+
+    monkeypatch.setattr(pop_factory, "datetime", FixedDatetime)
+    captured = {}
+
+    def fake_output(self, control_size, test_size, male_odds, level):
+        groups = pop_factory.PopulationFactory.pick_deleterious_groups(list(self.deleterious.values()), test_size)
+        captured["fam"] = self.generate_fam_file(control_size, test_size, male_odds, groups)
+        captured["header"] = pop_factory.gen_vcf_header(captured["fam"])
+
+    monkeypatch.setattr(pop_factory.PopulationFactory, "output_vcf_population", fake_output)
+    snps_gz = tmp_path / "snps_in.json.gz"
+    with open(os.path.join(src, "snps.json"), "rb") as f, gzip.open(snps_gz, "wb") as g:
+        g.write(f.read())
+    random.seed(meta["python_random_seed"])
+    out = tmp_path / "out"
+    pop_factory.main(meta["args"] + ["--snps_file", str(snps_gz), "--deleterious_file", os.path.join(src, "deleterious.json"),
+                                     "--outdir", str(out)])
+    for name in ("population.fam", "pop_deleterious.txt"):
+        assert (out / name).read_bytes() == open(os.path.join(gold, name), "rb").read(), name
+    with gzip.open(os.path.join(gold, "population.vcf.rows.gz"), "rb") as f:
+        vcf = f.read()
+    assert vcf.startswith(captured["header"].encode())
+    assert [s.person_id for s in captured["fam"]][:2] == [100301, 100302] and captured["fam"][0].family_id == 601
+
+
+def test_slices_of_the_snp_table_and_overrides():
+    """What a rank of `--gpus N` uploads: its own rows, offsets rebased, overrides made local."""
+    from dna_factory_b200 import host
+    case = load_case("mixed64")
+    flat = host.flatten_snps(case.snps)
+    orow, osamp = host.override_pairs(case.samples, case.snps)
+    S = len(case.snps)
+    pieces, opieces = [], 0
+    for lo, hi in ((0, 7), (7, 7), (7, S)):
+        a = host.slice_snps(flat, lo, hi)
+        assert len(a["chrom_class"]) == hi - lo == len(a["prefix_off"]) - 1 and a["prefix_off"][0] == 0
+        pieces.append(bytes(a["prefix_bytes"][:int(a["prefix_off"][-1])]))
+        assert np.array_equal(a["thresholds"], flat["thresholds"][lo:hi])
+        r, s = host.slice_overrides(orow, osamp, lo, hi)
+        assert all(0 <= int(x) < hi - lo for x in r)
+        opieces += len(r)
+    assert b"".join(pieces) == bytes(flat["prefix_bytes"][:int(flat["prefix_off"][-1])])
+    assert opieces == len(orow) > 0
+
+
+def test_override_pairs_table_handles_duplicate_ids_and_odd_keys():
+    from types import SimpleNamespace
+    from dna_factory_b200 import host
+    table = SimpleNamespace(ids=np.array([5, 9, 5, 12], dtype=np.int64))
+    fam = [SimpleNamespace(is_control=True, deleterious_snps={5: 1.0}),
+           SimpleNamespace(is_control=False, deleterious_snps={5: 0.5, "9": 0.5, 12.0: 0.1, 7: 0.2, True: 0.3, 9.5: 0.1}),
+           SimpleNamespace(is_control=False, deleterious_snps=None),
+           SimpleNamespace(is_control=False, deleterious_snps={9: 0.5})]
+    rows, samples = host.override_pairs_table(fam, table, row_base=100)
+    assert list(zip(rows.tolist(), samples.tolist())) == [(100, 1), (101, 3), (102, 1), (103, 1)]
+
+
+def test_tabix_rows_are_validated_up_front():
+    from dna_factory_b200 import tabix
+    tabix.validate_rows([0, 0, 1, 1], [5, 9, 1, 1])
+    tabix.validate_rows([], [])
+    for chrom, pos in (([0, 1, 0], [1, 2, 3]), ([0, 0], [9, 5]), ([0], [1 << 30]), ([0], [-1])):
+        with pytest.raises(ValueError):
+            tabix.validate_rows(chrom, pos)
+
+
+def test_chi_square_tail_known_answers():
+    """chi2_sf replaces scipy.stats.chi2.sf (whose import costs minutes on a cold box); values from scipy 1.x."""
+    from dna_factory_b200.allele_stats import chi2_sf
+    for x, k, want in ((5064.3, 5049, 0.4369388816951934), (2458.0, 2475, 0.5920034834051018), (100.0, 51, 4.998131371998267e-05),
+                       (20.0, 51, 0.9999710569766698), (3.0, 1, 0.08326451666355042), (60.0, 1, 9.485737571073857e-15),
+                       (5600, 5049, 5.7232768619912364e-08), (0.5, 3, 0.9188914116546758)):
+        assert abs(chi2_sf(x, k) - want) <= 1e-9 * max(want, 1e-6), (x, k)
+
+
+def test_bgzf_inflater_checks_every_block():
+    import zlib
+    from dna_factory_b200.allele_stats import inflate_bgzf
+    from oracle import oracle
+    text = (b"1\t100\trs1\tA\tC\t40\tPASS\t.\tGT\t" + b"0/1\t" * 5000 + b"\n") * 9
+    blob = oracle.bgzf(text, level=6, with_eof=False)
+    assert inflate_bgzf(blob) == text
+    bad = bytearray(blob)
+    bad[-6] ^= 1                                   # CRC32 of the last block
+    with pytest.raises(ValueError):
+        inflate_bgzf(bytes(bad))
+
+
+def test_reference_copy_is_byte_identical_and_runs():
+    """oracle/make_ref.py materialises the UNMODIFIED reference for the CPU baselines; where /root/reference is
+    mounted the copy must match it byte for byte and its CLI must run under the shims."""
+    import hashlib
+    from oracle import make_ref, ref_cli
+    if not os.path.exists(os.path.join(make_ref.REFERENCE_DIR, "pop_factory.py")):
+        pytest.skip("reference tree not mounted")
+    assert make_ref.materialise()
+    man = json.load(open(os.path.join(make_ref.DEST, "MANIFEST.json")))["sha256"]
+    for rel, digest in man.items():
+        assert hashlib.sha256(open(os.path.join(make_ref.REFERENCE_DIR, rel), "rb").read()).hexdigest() == digest
+        assert hashlib.sha256(open(os.path.join(make_ref.DEST, rel), "rb").read()).hexdigest() == digest
+    r = ref_cli.run(20, 20, 300, 2, procs=2)
+    assert r["calls"] == 12000 and r["write_s"] > 0 and r["vcf_bytes"] > 1000
