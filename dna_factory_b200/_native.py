@@ -81,7 +81,7 @@ def load():
         "dnaf_generate_device": (i32, [vp, u64, u64, u64, i32, sp]),
         "dnaf_genotypes": (i32, [vp, u64, u64, u64, u8p, u64]),
         "dnaf_text": (i32, [vp, u64, u64, u64, u8p, u64, u64p]),
-        "dnaf_bgzf_compress": (i32, [vp, u8p, u64, i32, u8p, u64, sp]),
+        "dnaf_bgzf_compress": (i32, [vp, u8p, u64, u8p, u64, sp]),
         "dnaf_bgzf_bound": (u64, [u64]),
         "dnaf_bgzf_eof": (i32, [u8p]),
         "dnaf_bgzf_scan": (i32, [u8p, u64, u32p, u32p, u64, u64p]),
@@ -300,13 +300,13 @@ class Engine:
         self._check(self._lib.dnaf_text(self._h, row_begin, row_end, seed, _u8(out), out.nbytes, ctypes.byref(n)))
         return out[:n.value].tobytes()
 
-    def bgzf_compress(self, data, level=6):
+    def bgzf_compress(self, data):
         buf = np.frombuffer(bytes(data) + b"\0", dtype=np.uint8)
         n = len(buf) - 1
         bound = int(self._lib.dnaf_bgzf_bound(n))
         out = np.empty(bound, dtype=np.uint8)
         st = Stats()
-        self._check(self._lib.dnaf_bgzf_compress(self._h, _u8(buf), n, level, _u8(out), bound, ctypes.byref(st)))
+        self._check(self._lib.dnaf_bgzf_compress(self._h, _u8(buf), n, _u8(out), bound, ctypes.byref(st)))
         return out[:st.bgzf_bytes].tobytes(), st.as_dict()
 
 

@@ -600,10 +600,9 @@ int dnaf_text(dnaf_ctx* c, uint64_t row_begin, uint64_t row_end, uint64_t seed, 
     return DNAF_OK;
 }
 
-int dnaf_bgzf_compress(dnaf_ctx* c, const uint8_t* text, uint64_t n, int level, uint8_t* out, uint64_t cap,
+int dnaf_bgzf_compress(dnaf_ctx* c, const uint8_t* text, uint64_t n, uint8_t* out, uint64_t cap,
                        dnaf_stats* stats) {
     if (!c) return DNAF_E_ARG;
-    if (level < 1 || level > 9) return fail(c, DNAF_E_ARG, "level must be 1..9");
     if (n && !text) return fail(c, DNAF_E_ARG, "text is NULL");
     CU(c, cudaSetDevice(c->dev));
     dnaf_stats local;

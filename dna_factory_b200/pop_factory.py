@@ -84,7 +84,7 @@ class BgzfSink:
 
     def flush(self):
         if self._pending:
-            blob, _ = self._engine.bgzf_compress(b"".join(self._pending), level=self.compresslevel)
+            blob, _ = self._engine.bgzf_compress(b"".join(self._pending))
             self._pending = []
             self._handle.write(blob)
             if self.index is not None:
@@ -312,7 +312,7 @@ class PopulationFactory:
                 print("%s Finished work chunk 1 of 1." % datetime.now().strftime("%Y-%m-%d %H:%M"), flush=True)
             if self.tbi:
                 # what `bcftools index -t` (README.md:98-99) would derive by inflating the file again
-                blob, _ = engine.bgzf_compress(f.index.payload(), level=6)
+                blob, _ = engine.bgzf_compress(f.index.payload())
                 with open(main_file + ".tbi", "wb") as t:
                     t.write(blob + _native.bgzf_eof())
         finally:

@@ -195,9 +195,10 @@ int dnaf_genotypes(dnaf_ctx* ctx, uint64_t row_begin, uint64_t row_end, uint64_t
 int dnaf_text(dnaf_ctx* ctx, uint64_t row_begin, uint64_t row_end, uint64_t seed, uint8_t* out, uint64_t out_cap,
               uint64_t* n_bytes);
 
-/* BgzfWriter.write() for arbitrary bytes (used for the VCF header, pop_factory.py:404-405):
- * cuts `text` every 65280 bytes and encodes each piece on the GPU.  No EOF block. */
-int dnaf_bgzf_compress(dnaf_ctx* ctx, const uint8_t* text, uint64_t n_bytes, int level, uint8_t* out,
+/* BgzfWriter.write() for arbitrary bytes (used for the VCF header, pop_factory.py:404-405, and the .tbi payload):
+ * cuts `text` every 65280 bytes and encodes each piece on the GPU with the generic encoder (byte-4-back parse,
+ * per-block dynamic Huffman).  It has one parse, so it takes no level (ABI 4 accepted and ignored one).  No EOF block. */
+int dnaf_bgzf_compress(dnaf_ctx* ctx, const uint8_t* text, uint64_t n_bytes, uint8_t* out,
                        uint64_t out_cap, dnaf_stats* stats);
 uint64_t dnaf_bgzf_bound(uint64_t text_bytes);
 /* Block table of a BGZF stream held in host memory (no GPU work, no context): compressed and text size of
