@@ -516,43 +516,40 @@ def main():
     # last rank's window against the CPU oracle as well.
     multi_gpu_parity = None
     if world > 1:
-        import zlib
         W = 24
         blob, st_w = eng.generate(0, W, PHILOX_SEED, level=args.level)
-        text = _inflate_bgzf(blob)
-        mine = torch.tensor([len(text), st_w["bgzf_blocks"], zlib.crc32(text), st_w["crc_xor"]], dtype=torch.int64, device="cuda")
-        allv = [torch.zeros_like(mine) for _ in range(world)]
-        dist.all_gather(allv, mine)
-        if rank == 0:
-            ok, why = True, ""
-            bounds = partition.row_bounds(TOTAL_SNPS, world)
-            for r in range(world):
-                sex_r, ctl_r, table_r, orow_r, osamp_r = synth_population(R, r, window=R)
-                chk = _native.Engine(local_rank)
-                chk.set_samples(sex_r, ctl_r)
-                chk.set_snps(**host.slice_snps(table_r.device_arrays(), 0, W))
-                chk.set_overrides(*host.slice_overrides(orow_r, osamp_r, 0, W))
-                chk.set_row_base(bounds[r])
-                b2, st2 = chk.generate(0, W, PHILOX_SEED, level=args.level)
-                t2 = _inflate_bgzf(b2)
-                got = [int(x) for x in allv[r].tolist()]
-                if got != [len(t2), st2["bgzf_blocks"], zlib.crc32(t2), st2["crc_xor"]]:
-                    ok, why = False, "rank %d window differs from its single-GPU recomputation" % r
-                if r == world - 1 and ok:
-                    from oracle import oracle
-                    from types import SimpleNamespace
-                    fam = [SimpleNamespace(sex=int(a), is_control=bool(c), deleterious_snps=None if c else {}, person_id=i)
-                           for i, (a, c) in enumerate(zip(sex_r, ctl_r))]
-                    flat = oracle.flatten(fam, [table_r.snp(q) for q in range(W)])
-                    o_r, o_s = host.slice_overrides(orow_r, osamp_r, 0, W)
-                    flat["over_row"], flat["over_sample"] = o_r, o_s
-                    want, _ = oracle.rows_from_flat(flat, PHILOX_SEED, bounds[r], n_threads=8)
-                    if want.tobytes() != t2:
-                        ok, why = False, "rank %d window differs from the CPU oracle" % r
-                chk.close()
-            multi_gpu_parity = "ok" if ok else "FAILED: " + why
-            if not ok:
-                raise SystemExit("multi-GPU parity check failed: " + why)
+        mine = partition.window_signature(_inflate_bgzf(blob), st_w["bgzf_blocks"], st_w["crc_xor"])
+        bounds = partition.row_bounds(TOTAL_SNPS, world)
+        last_text = {}
+
+        def recompute(r):   # runs on rank 0 only
+            sex_r, ctl_r, table_r, orow_r, osamp_r = synth_population(R, r, window=R)
+            chk = _native.Engine(local_rank)
+            chk.set_samples(sex_r, ctl_r)
+            chk.set_snps(**host.slice_snps(table_r.device_arrays(), 0, W))
+            chk.set_overrides(*host.slice_overrides(orow_r, osamp_r, 0, W))
+            chk.set_row_base(bounds[r])
+            b2, st2 = chk.generate(0, W, PHILOX_SEED, level=args.level)
+            chk.close()
+            t2 = _inflate_bgzf(b2)
+            if r == world - 1:
+                last_text.update(text=t2, pop=(sex_r, ctl_r, table_r, orow_r, osamp_r))
+            return partition.window_signature(t2, st2["bgzf_blocks"], st2["crc_xor"])
+
+        multi_gpu_parity = partition.check_rank_windows(mine, recompute, dist, "cuda")
+        if rank == 0 and multi_gpu_parity == "ok":      # and the last rank's window against the CPU oracle
+            from oracle import oracle
+            from types import SimpleNamespace
+            sex_r, ctl_r, table_r, orow_r, osamp_r = last_text["pop"]
+            fam = [SimpleNamespace(sex=int(a), is_control=bool(c), deleterious_snps=None if c else {}, person_id=i)
+                   for i, (a, c) in enumerate(zip(sex_r, ctl_r))]
+            flat = oracle.flatten(fam, [table_r.snp(q) for q in range(W)])
+            flat["over_row"], flat["over_sample"] = host.slice_overrides(orow_r, osamp_r, 0, W)
+            want, _ = oracle.rows_from_flat(flat, PHILOX_SEED, bounds[world - 1], n_threads=8)
+            if want.tobytes() != last_text["text"]:
+                multi_gpu_parity = "FAILED: rank %d window differs from the CPU oracle" % (world - 1)
+        if rank == 0 and multi_gpu_parity != "ok":
+            raise SystemExit("multi-GPU parity check failed: " + str(multi_gpu_parity))
 
     # ------------------------------------------------------------------ extras (rank 0 of a 1-GPU run)
     extras = {}
