@@ -47,11 +47,11 @@ struct LzCfg {
 
 // -z level -> parse parameters.  3: the two near distances only (no tables are built); 4..9: zlib's own ladder shape
 // (its max_chain is 16 / 32 / 128 / 256 / 1024 / 4096 there; shorter here because every chain entry is already a
-// >= 2*key byte match), lazy evaluation from 6 on.
+// >= 2*key byte match), lazy evaluation from 6 on; like zlib, the lookup behind a match searches a quarter as deep.
 __host__ __device__ inline LzCfg lz_cfg(int level, uint32_t key) {
     LzCfg c;
     c.key = key;
-    c.chain = level <= 3 ? 0u : level == 4 ? 1u : level == 5 ? 4u : level == 6 ? 16u : level == 7 ? 32u : level == 8 ? 64u : 128u;
+    c.chain = level <= 3 ? 0u : level == 4 ? 1u : level == 5 ? 4u : level == 6 ? 20u : level == 7 ? 32u : level == 8 ? 64u : 128u;
     c.lazy = level >= 6 ? 1u : 0u;
     c.nice = level <= 4 ? 16u : level == 5 ? 32u : level <= 7 ? 64u : 128u;   // zlib: 16, 32, 128, 128, 258, 258 bytes
     return c;
@@ -191,7 +191,8 @@ __host__ __device__ __forceinline__ void lz_span_tokens(const Mem& mem, uint32_t
             const uint32_t key = (ws0 & kmask) | ((s & 1u) << cfg.key);
             uint32_t reg = s / kLzRegion;
             uint32_t j = mem.prev(s);
-            for (uint32_t n = 0; n < cfg.chain; ++n) {
+            const uint32_t depth = held ? (cfg.chain + 3u) >> 2 : cfg.chain;   // zlib: a lookup behind a good match searches a quarter as deep
+            for (uint32_t n = 0; n < depth; ++n) {
                 while (j == kLzNone && reg) {
                     --reg;
                     j = mem.head(reg, key);
