@@ -37,6 +37,7 @@ constexpr uint32_t kLzNone = 0xFFFFu;      // prev[] entry / head value of "no e
 constexpr uint32_t kLzRegion = 4096;   // alleles per region (one warp's 32 spans)
 constexpr uint32_t kLzMaxKey = 9;      // alleles in a key (head tables have 2^(key+1) 32-bit entries per region)
 constexpr uint32_t kLzMaxDist = 16384; // alleles = 32768 bytes
+constexpr uint32_t kLzGood = 8;        // alleles: with a near match this long (or behind a match) the chain is searched a quarter as deep
 
 struct LzCfg {
     uint32_t chain;   // far candidates examined per lookup
@@ -191,7 +192,7 @@ __host__ __device__ __forceinline__ void lz_span_tokens(const Mem& mem, uint32_t
             const uint32_t key = (ws0 & kmask) | ((s & 1u) << cfg.key);
             uint32_t reg = s / kLzRegion;
             uint32_t j = mem.prev(s);
-            const uint32_t depth = held ? (cfg.chain + 3u) >> 2 : cfg.chain;   // zlib: a lookup behind a good match searches a quarter as deep
+            const uint32_t depth = (held || best_k >= kLzGood) ? (cfg.chain + 3u) >> 2 : cfg.chain;   // zlib: a lookup behind / with a good match searches a quarter as deep
             for (uint32_t n = 0; n < depth; ++n) {
                 while (j == kLzNone && reg) {
                     --reg;
