@@ -292,6 +292,11 @@ def main():
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # debugging aid: DNAF_BENCH_ONE_GPU=1 runs all ranks of a torchrun launch on GPU 0 over gloo, so that the N > 1
+    # code path (ranges, reductions, multi_gpu_parity) can be exercised on a 1-GPU box; such a line is not a result
+    shared_gpu = os.environ.get("DNAF_BENCH_ONE_GPU") == "1"
+    if shared_gpu:
+        local_rank = 0
     world = int(os.environ.get("WORLD_SIZE", "1"))
     warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -325,7 +330,11 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: dna_factory_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        if shared_gpu:
+            dist.init_process_group("gloo")
+        else:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    red_dev = "cpu" if shared_gpu else "cuda"
 
     R = args.rows_per_step
     n_steps_total = warmup + args.steps
@@ -351,10 +360,10 @@ def main():
         torch.cuda.synchronize()
 
     def max_over_ranks(x):
-        return partition.reduce_max(x, dist if world > 1 else None, "cuda")
+        return partition.reduce_max(x, dist if world > 1 else None, red_dev)
 
     def sum_over_ranks(x):
-        return partition.reduce_sum(x, dist if world > 1 else None, "cuda")
+        return partition.reduce_sum(x, dist if world > 1 else None, red_dev)
 
     _lap("population + context ready")
     # ------------------------------------------------------------------ device-resident pass (`value`)
@@ -536,7 +545,7 @@ def main():
                 last_text.update(text=t2, pop=(sex_r, ctl_r, table_r, orow_r, osamp_r))
             return partition.window_signature(t2, st2["bgzf_blocks"], st2["crc_xor"])
 
-        multi_gpu_parity = partition.check_rank_windows(mine, recompute, dist, "cuda")
+        multi_gpu_parity = partition.check_rank_windows(mine, recompute, dist, red_dev)
         if rank == 0 and multi_gpu_parity == "ok":      # and the last rank's window against the CPU oracle
             from oracle import oracle
             from types import SimpleNamespace
@@ -582,6 +591,8 @@ def main():
                         "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                 "compression_ratio": text_bytes / max(1, bgzf_bytes), "text_gb_per_s": text_bytes / (ms * 1e-3) / 1e9}
+        if shared_gpu:
+            line["debug"] = "DNAF_BENCH_ONE_GPU=1: every rank ran on GPU 0 over gloo -- plumbing check, not a result"
         _lap("cpu baselines")
         if cpu_port is not None:
             line["cpu_baseline_port"] = cpu_port

@@ -36,7 +36,7 @@ class DnafError(RuntimeError):
 
 # every symbol include/dnaf_b200.h declares (tests check the built library exports all of them)
 ABI_VERSION = 5   # include/dnaf_b200.h DNAF_ABI_VERSION
-EXPORTS = ["dnaf_abi_version", "dnaf_last_error", "dnaf_create", "dnaf_destroy", "dnaf_set_stream",
+EXPORTS = ["dnaf_abi_version", "dnaf_device_count", "dnaf_last_error", "dnaf_create", "dnaf_destroy", "dnaf_set_stream",
            "dnaf_set_chunk_bytes", "dnaf_set_row_base", "dnaf_set_fused", "dnaf_set_samples", "dnaf_set_snps", "dnaf_set_overrides",
            "dnaf_plan", "dnaf_row_offsets", "dnaf_generate", "dnaf_generate_stream", "dnaf_generate_fd", "dnaf_generate_fd_at", "dnaf_generate_device", "dnaf_genotypes",
            "dnaf_text", "dnaf_bgzf_compress", "dnaf_bgzf_bound", "dnaf_bgzf_eof", "dnaf_bgzf_scan", "dnaf_block_log",
@@ -62,6 +62,7 @@ def load():
     sp = ctypes.POINTER(Stats)
     sig = {
         "dnaf_abi_version": (i32, []),
+        "dnaf_device_count": (i32, []),
         "dnaf_last_error": (ctypes.c_char_p, [vp]),
         "dnaf_create": (i32, [i32, ctypes.POINTER(vp)]),
         "dnaf_destroy": (None, [vp]),
@@ -107,6 +108,11 @@ def load():
                           % (LIB_PATH, L.dnaf_abi_version(), ABI_VERSION))
     _lib = L
     return L
+
+
+def device_count():
+    """CUDA devices visible to the process."""
+    return int(load().dnaf_device_count())
 
 
 def _u8(a):

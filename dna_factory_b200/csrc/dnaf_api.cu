@@ -46,6 +46,15 @@ extern "C" {
 
 int dnaf_abi_version(void) { return DNAF_ABI_VERSION; }
 
+int dnaf_device_count(void) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return count;
+}
+
 const char* dnaf_last_error(const dnaf_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
 int dnaf_create(int device_ordinal, dnaf_ctx** out) {

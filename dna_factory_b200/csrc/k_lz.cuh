@@ -139,13 +139,66 @@ __host__ __device__ __forceinline__ uint32_t lz_extend(const Mem& mem, uint32_t 
     }
 }
 
-// One trip of the loop = one LOOKUP (at byte p, for allele s) and the token it ends in.  The lanes of a warp stay
-// together at that granularity: set-up and the two near distances (4 and 8 bytes: j = s-2, s-4, compared from the
-// same three words that hold s's own window), then the key chain of s nearest first (own region, then the regions
-// before it through their heads), then ONE emit.  (Two earlier shapes were measured: nested per-token loops left
-// 18 of 32 threads active, a fully flat one-candidate-per-trip state machine 13 of 32 -- the lanes of a trip were in
-// different states and the warp ran every state's code.)
-// nice: a match of that many alleles ends the search (zlib's nice_length).
+// Best match at allele s (k alleles at distance `da` alleles; k = 0: none), and s's own 32-allele window.
+// Set-up and the two near distances (4 and 8 bytes: j = s-2, s-4) are compared from the same three words that hold
+// s's own window, then the key chain of s is walked nearest first (own region, then the regions before it through
+// their heads), at most `depth` entries (a quarter of it once a match of kLzGood alleles is in hand).
+template <class Mem>
+__host__ __device__ __forceinline__ void lz_lookup(const Mem& mem, uint32_t s, uint32_t aend, uint32_t nall, const LzCfg cfg,
+                                                  uint32_t depth, uint32_t& best_k, uint32_t& best_da, uint32_t& ws0) {
+    const uint32_t limit = aend - s;
+    // alleles lo .. lo+63 with lo = s - 4 (s >= 4 everywhere but in the first cells of a block)
+    const uint32_t lo = s >= 4u ? s - 4u : 0u, sh0 = s - lo;
+    const uint32_t w = lo >> 5, sh = lo & 31u;
+    const uint32_t x0 = mem.word(w), x1 = mem.word(w + 1u), x2 = mem.word(w + 2u);
+    const uint32_t v0 = lz_fsr(x0, x1, sh), v1 = lz_fsr(x1, x2, sh);
+    ws0 = lz_fsr(v0, v1, sh0);
+    const uint32_t room = limit < 32u ? limit : 32u;
+    uint32_t k1 = 0, k2 = 0;
+    if (s >= 2u) {
+        const uint32_t d1 = ws0 ^ lz_fsr(v0, v1, sh0 - 2u);
+        k1 = d1 ? lz_ctz32(d1) : 32u;
+        k1 = k1 < room ? k1 : room;
+    }
+    if (s >= 4u) {
+        const uint32_t d2 = ws0 ^ v0;
+        k2 = d2 ? lz_ctz32(d2) : 32u;
+        k2 = k2 < room ? k2 : room;
+    }
+    best_k = k2 > k1 ? k2 : k1;
+    best_da = k2 > k1 ? 4u : 2u;
+    if (best_k == 32u && limit > 32u) best_k = lz_extend(mem, s, s - best_da, limit);   // the nearer one goes on
+    if (depth && best_k < limit && best_k < cfg.nice && s + cfg.key <= nall) {
+        if (best_k >= kLzGood) depth = (depth + 3u) >> 2;
+        const uint32_t key = (ws0 & ((1u << cfg.key) - 1u)) | ((s & 1u) << cfg.key);
+        uint32_t reg = s / kLzRegion;
+        uint32_t j = mem.prev(s);
+        for (uint32_t n = 0; n < depth; ++n) {
+            while (j == kLzNone && reg) {
+                --reg;
+                j = mem.head(reg, key);
+            }
+            if (j == kLzNone || s - j > kLzMaxDist) break;
+            const uint32_t x = ws0 ^ lz_win32(mem, j);
+            uint32_t k = x ? lz_ctz32(x) : 32u;
+            k = k < room ? k : room;
+            if (k == 32u && limit > 32u) k = lz_extend(mem, s, j, limit);
+            if (k > best_k) {
+                best_k = k;
+                best_da = s - j;
+                if (k >= limit || k >= cfg.nice) break;
+            }
+            j = mem.prev(j);
+        }
+    }
+}
+
+// One trip of the loop = one TOKEN: the lookup at byte p and, with lazy evaluation, the lookup one allele on (searched
+// a quarter as deep, zlib's rule behind a good match) -- both in the same trip, so that the lanes of a warp walk their
+// chains together.  (Earlier shapes, measured: nested per-token loops left 18 of 32 threads active; a fully flat
+// one-candidate-per-trip state machine 13 of 32 -- every trip ran the code of every state some lane was in; one lookup
+// per trip with the lazy second lookup as a trip of its own 16 of 32 at -z 6 -- full-depth and quarter-depth lanes
+// mixed.)  nice: a match of that many alleles ends the search (zlib's nice_length).
 template <class Mem, class Sink>
 __host__ __device__ __forceinline__ void lz_span_tokens(const Mem& mem, uint32_t a0, int nc, bool first_in_block, bool starts_row,
                                                         bool ends_row, bool ends_block, uint32_t nall, const LzCfg cfg, Sink& sink) {
@@ -160,83 +213,33 @@ __host__ __device__ __forceinline__ void lz_span_tokens(const Mem& mem, uint32_t
         p = 2 * (int)a0 + 3;
     }
     const int pend = 2 * (int)aend - 1;             // one past the span's last byte
-    const uint32_t kmask = (1u << cfg.key) - 1u;
-    // lazy evaluation: the finished lookup at the byte before (held while the next allele is examined)
-    uint32_t held_len = 0, held_da = 0;
-    bool held = false;
     while (p < pend) {
-        const uint32_t s = (uint32_t)(p + 1) >> 1;
-        const uint32_t limit = aend - s;             // s < aend here: the span's last byte is an allele
-        // alleles lo .. lo+63 with lo = s - 4 (s >= 4 everywhere but in the first cells of a block)
-        const uint32_t lo = s >= 4u ? s - 4u : 0u, sh0 = s - lo;
-        const uint32_t w = lo >> 5, sh = lo & 31u;
-        const uint32_t x0 = mem.word(w), x1 = mem.word(w + 1u), x2 = mem.word(w + 2u);
-        const uint32_t v0 = lz_fsr(x0, x1, sh), v1 = lz_fsr(x1, x2, sh);
-        const uint32_t ws0 = lz_fsr(v0, v1, sh0);
-        const uint32_t room = limit < 32u ? limit : 32u;
-        uint32_t k1 = 0, k2 = 0;
-        if (s >= 2u) {
-            const uint32_t d1 = ws0 ^ lz_fsr(v0, v1, sh0 - 2u);
-            k1 = d1 ? lz_ctz32(d1) : 32u;
-            k1 = k1 < room ? k1 : room;
-        }
-        if (s >= 4u) {
-            const uint32_t d2 = ws0 ^ v0;
-            k2 = d2 ? lz_ctz32(d2) : 32u;
-            k2 = k2 < room ? k2 : room;
-        }
-        uint32_t best_k = k2 > k1 ? k2 : k1;
-        uint32_t best_da = k2 > k1 ? 4u : 2u;
-        if (best_k == 32u && limit > 32u) best_k = lz_extend(mem, s, s - best_da, limit);   // the nearer one goes on
-        if (cfg.chain && best_k < limit && best_k < cfg.nice && s + cfg.key <= nall) {
-            const uint32_t key = (ws0 & kmask) | ((s & 1u) << cfg.key);
-            uint32_t reg = s / kLzRegion;
-            uint32_t j = mem.prev(s);
-            const uint32_t depth = (held || best_k >= kLzGood) ? (cfg.chain + 3u) >> 2 : cfg.chain;   // zlib: a lookup behind / with a good match searches a quarter as deep
-            for (uint32_t n = 0; n < depth; ++n) {
-                while (j == kLzNone && reg) {
-                    --reg;
-                    j = mem.head(reg, key);
-                }
-                if (j == kLzNone || s - j > kLzMaxDist) break;
-                const uint32_t x = ws0 ^ lz_win32(mem, j);
-                uint32_t k = x ? lz_ctz32(x) : 32u;
-                k = k < room ? k : room;
-                if (k == 32u && limit > 32u) k = lz_extend(mem, s, j, limit);
-                if (k > best_k) {
-                    best_k = k;
-                    best_da = s - j;
-                    if (k >= limit || k >= cfg.nice) break;
-                }
-                j = mem.prev(j);
-            }
-        }
+        const uint32_t s = (uint32_t)(p + 1) >> 1;   // s < aend here: the span's last byte is an allele
         const uint32_t odd = (uint32_t)p & 1u;
+        uint32_t best_k, best_da, ws0;
+        lz_lookup(mem, s, aend, nall, cfg, cfg.chain, best_k, best_da, ws0);
         // bytes p .. 2(s+k)-1, minus the separator after the span's last allele
         int len = 2 * (int)(s + best_k) - p - (s + best_k == aend ? 1 : 0);
-        if (held) {
-            // p is the byte after the held lookup's: take the literal + this match if that is longer
-            held = false;
-            if (len > (int)held_len + 1) {
-                sink.emit(false, bit(s - 1u), 0, 0);
-            } else {
-                len = (int)held_len;
-                best_da = held_da;
-                p -= 1;
+        bool lit_first = false;
+        if (cfg.lazy && len >= 3 && !odd && s + 1u < aend && s + best_k < aend && best_k < cfg.nice) {
+            // would a literal now buy a longer match from the next byte on?
+            uint32_t k2, da2, w2;
+            lz_lookup(mem, s + 1u, aend, nall, cfg, (cfg.chain + 3u) >> 2, k2, da2, w2);
+            const int len2 = 2 * (int)(s + 1u + k2) - (p + 1) - (s + 1u + k2 == aend ? 1 : 0);
+            if (len2 > len + 1) {
+                lit_first = true;
+                len = len2;
+                best_da = da2;
             }
-            sink.emit(true, 0, len, 2 * (int)best_da);
-            p += len;
-        } else if (len >= 3 && cfg.lazy && !odd && s + 1u < aend && s + best_k < aend && best_k < cfg.nice) {
-            held = true;                             // would a literal now buy a longer match from the next byte on?
-            held_len = (uint32_t)len;
-            held_da = best_da;
-            p += 1;
-        } else {
-            const bool is_match = len >= 3;
-            const int id = odd ? ((s & 1u) ? kLitSlash : kLitTab) : (int)((ws0 & 1u));   // separator before allele s / allele s
-            sink.emit(is_match, id, len, 2 * (int)best_da);
-            p += is_match ? len : 1;
         }
+        if (lit_first) {
+            sink.emit(false, (int)(ws0 & 1u), 0, 0);
+            p += 1;
+        }
+        const bool is_match = len >= 3;
+        const int id = odd ? ((s & 1u) ? kLitSlash : kLitTab) : (int)(ws0 & 1u);   // separator before allele s / allele s
+        sink.emit(is_match, id, len, 2 * (int)best_da);
+        p += is_match ? len : 1;
     }
     if (ends_row) sink.emit(false, kLitNl, 0, 0);
     if (ends_block) sink.eob();

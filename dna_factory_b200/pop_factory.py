@@ -373,6 +373,7 @@ class PopulationFactory:
         nothing is spooled or copied twice.  Every rank holds only its own slice of the SNP table; the Philox row
         counter of its local row r is bounds[g] + r (dnaf_set_row_base)."""
         bounds = partition.row_bounds(n_rows, gpus)
+        n_dev = max(1, _native.device_count())      # more ranks than devices: ranks share devices round-robin
         errors = []
         index = getattr(file, "index", None)
         blocks, row_off, sizes, engines = [None] * gpus, [None] * gpus, [0] * gpus, [None] * gpus
@@ -384,7 +385,7 @@ class PopulationFactory:
         def run(g):
             try:
                 lo, hi = bounds[g], bounds[g + 1]
-                eng = engines[g] = _native.Engine(g)
+                eng = engines[g] = _native.Engine(g % n_dev)
                 eng.set_samples(sex, ctl)
                 eng.set_snps(**host.slice_snps(arrays, lo, hi))
                 eng.set_overrides(*host.slice_overrides(orow, osamp, lo, hi))

@@ -69,6 +69,9 @@ typedef struct dnaf_stats {
 } dnaf_stats;
 
 int dnaf_abi_version(void);
+/* CUDA devices visible to the process (0 when there is none or the driver is missing): lets the host spread the
+ * contiguous SNP ranges of a multi-GPU run (pop_factory.py:426 stripes over worker processes) over what exists. */
+int dnaf_device_count(void);
 const char* dnaf_last_error(const dnaf_ctx* ctx); /* ctx may be NULL: error of the last failed create */
 
 /* Replaces the worker pool set-up of write_vcf_snps (pop_factory.py:419-434). */
