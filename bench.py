@@ -57,16 +57,19 @@ def synth_population(n_rows, rank=0, window=ROWS_PER_STEP):
     # every step's row window is its own sorted draw from the genome-wide distribution, so each step sees the
     # whole-job chromosome mix (about 4.8 % X and 0.25 % Y rows) instead of ROWS_PER_STEP rows of chromosome 1
     fac = snp.SnpFactory.init_from_cdf_file()
-    wins = []
+    wins, orows, osamps = [], [], []
     for w0 in range(0, n_rows, window):
-        t = fac.random_snp_table(min(window, n_rows - w0), min_maf=MIN_MAF, vector_alt=True).sorted()
+        wn = min(window, n_rows - w0)
+        t = fac.random_snp_table(wn, min_maf=MIN_MAF, vector_alt=True).sorted()
         t.ids = t.ids + w0
         wins.append(t)
+        # polygenic overrides: ~6 deleterious SNPs per case over the whole job, as deleterious.yml's groups produce;
+        # drawn window by window, so that a window's forced cells do not depend on how many windows follow it
+        n_over = 6 * N_CASES * wn // TOTAL_SNPS + 2
+        orows.append(np.sort(np.random.randint(w0, w0 + wn, n_over)).astype(np.uint64))
+        osamps.append(np.random.randint(N_CONTROLS, n, n_over).astype(np.uint32))
     table = snp.SnpTable.concat(wins)
-    # polygenic overrides: ~6 deleterious SNPs per case, as deleterious.yml's groups produce
-    n_over = 6 * N_CASES * n_rows // TOTAL_SNPS + 8
-    orow = np.sort(np.random.randint(0, n_rows, n_over)).astype(np.uint64)
-    osamp = np.random.randint(N_CONTROLS, n, n_over).astype(np.uint32)
+    orow, osamp = np.concatenate(orows), np.concatenate(osamps)
     np.random.set_state(rs_state)
     return sex, ctl, table, orow, osamp
 
@@ -526,6 +529,9 @@ def main():
     multi_gpu_parity = None
     if world > 1:
         W = 24
+        eng.set_snps(**host.slice_snps(arrays, 0, W))     # the e2e pass left one of its steps in the context
+        eng.set_overrides(*host.slice_overrides(orow, osamp, 0, W))
+        eng.set_row_base(row_base)
         blob, st_w = eng.generate(0, W, PHILOX_SEED, level=args.level)
         mine = partition.window_signature(_inflate_bgzf(blob), st_w["bgzf_blocks"], st_w["crc_xor"])
         bounds = partition.row_bounds(TOTAL_SNPS, world)
