@@ -500,11 +500,11 @@ def main():
                        batches[warmup:]]))
     d2h = int(np.mean([s["bgzf_bytes"] for s in e2e_stats]))
     launches += 0  # e2e launches are outside the `value` region
-    # the same end-to-end steps at the reference's default -z 6 and at -z 4: past one GPU the host's PCIe fabric bounds
+    # the same end-to-end steps at the reference's default -z 6 and at -z 4 / 5: past one GPU the host's PCIe fabric bounds
     # the rate, so fewer compressed bytes per call are worth more than kernel time (BASELINE config 5 at 1/2/4/8 GPUs)
     e2e_by_level = {str(args.level): e2e_calls / e2e_s}
     if not args.no_extras:
-        for lv in (4, 6):
+        for lv in (4, 5, 6):
             if lv == args.level:
                 continue
             e2e_level[0] = lv
