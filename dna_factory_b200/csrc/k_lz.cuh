@@ -1,18 +1,18 @@
-// k_lz: the autosome-row kernel of the higher compression tiers (-z 4..9).  Same job, block geometry, draws, CRC
+// k_lz: the autosome-row kernel of the higher compression tiers (-z 3..9).  Same job, block geometry, draws, CRC
 // and output slots as k_auto (k_auto.cuh); what changes is the deflate parse.  k_auto predicts every byte by the byte
 // 4 back ("P4"); here a block is parsed with real LZ77 matches over its whole 32 KiB window -- in the ALLELE-BIT
 // domain: the text of an autosome row is  a0 '/' a1 '\t' ...  with a_j in {'0','1'}, so the block is a string of
 // allele bits with fixed separators, and a deflate match (length 2k [+1], distance 4D bytes) is a run of k equal bits
-// 2D positions back.  Comparing 64 alleles (128 text bytes) costs one 64-bit XOR.
+// 2D positions back.  Comparing 32 alleles (64 text bytes) costs one XOR and one find-first-set.
 //
 // Reference behaviour restated: Bio.bgzf.BgzfWriter(compresslevel=z) -- pop_factory.py:403 passes the -z value
 // (default 6, pop_factory.py:656-658) to zlib.compressobj(level, DEFLATED, -15) for every 64 KiB block.  zlib's
-// levels are hash chains of growing depth (4, 8, 16, 32, 128, 4096 candidates at levels 4, 5, 6, 7, 8, 9; lazy
-// evaluation from level 4 on); the tiers here follow that ladder (LzCfg).  Compressed bytes are outside the parity
+// levels are hash chains of growing depth (16, 32, 128, 256, 1024, 4096 candidates at levels 4 .. 9, lazy
+// evaluation from level 4 on); the tiers here follow that ladder (lz_cfg).  Compressed bytes are outside the parity
 // contract; the decompressed text is identical at every level.
 //
 // Match finder (deterministic, built per block in shared memory):
-//   * key of allele position a = its next L alleles (L <= 10, per MAF bucket) and a's parity (distances are even)
+//   * key of allele position a = its next L alleles (L = 8 or 9, per MAF bucket) and a's parity (distances are even)
 //   * a block is cut into REGIONS of 4096 alleles = the 32 spans of one warp.  Every warp links the positions of its
 //     region into per-key chains in position order, 32 consecutive positions per step: every lane reads
 //     head[region][key] (the last occurrence before this step) into prev[a], then the step's positions go into the
@@ -25,8 +25,10 @@
 //   * a lookup at position s walks prev[] in its own region, then enters the regions before it through their heads
 //     (all of a previous region precedes s): candidates come nearest first, like zlib's hash chains, at most
 //     `chain` of them; plus the two near distances 4 and 8 bytes that need no table.
-//   * one thread parses one span (64 cells) sequentially, greedy longest match (ties: nearest), optional one-step
-//     lazy evaluation; tokens never cross spans, sources may lie anywhere earlier in the block.
+//   * one thread parses one span (64 cells) sequentially, greedy longest match (ties: nearest), one-step lazy
+//     evaluation from -z 6 on; tokens never cross spans, sources may lie anywhere earlier in the block.
+//   * per MAF bucket the host fits the codes of this parse AND of the near-distances-only parse and keeps the
+//     smaller (fused_host.h make_lz_table): blocks of such buckets (LzTable.chain == 0) skip the chain build.
 #pragma once
 #include "k_auto.cuh"
 
