@@ -30,6 +30,7 @@
 #include "k_select.cuh"
 #include "snps_json.h"
 #include <map>
+#include <mutex>
 #include <unordered_map>
 
 using namespace dnaf;
@@ -202,6 +203,11 @@ int dnaf_set_samples(dnaf_ctx* c, uint32_t n, const uint8_t* sex, const uint8_t*
     c->h_sex.assign(sex, sex + n);
     c->h_xoff = xoff;
     c->samples_epoch++;
+    {
+        uint64_t h = 1469598103934665603ull ^ n;
+        for (uint32_t i = 0; i < n; ++i) h = (h ^ sex[i]) * 1099511628211ull;
+        c->samples_hash = h;
+    }
     c->h_xspans = hosttab::build_xspans(sex, n, xoff.data());
     rc = upload(c, c->d_xspans, c->h_xspans.data(), c->h_xspans.size());
     if (rc) return rc;

@@ -61,6 +61,18 @@ uint32_t host_mulmod(uint32_t a, uint32_t b) {
 
 }  // namespace
 
+// Code tables are pure functions of (MAF bucket, prefix byte model, spans per block, sample set[, level]): one cache per
+// PROCESS, so that the contexts of a multi-GPU run (one per rank, pop_factory --gpus N) build every table once
+// between them instead of once each (8 ranks x ~10 s of host CPU on a C4-shaped population).  g_tables_mu is held
+// by ensure_tables / ensure_lz_tables while they look up, build and insert.
+namespace {
+std::mutex g_tables_mu;
+std::map<std::pair<uint64_t, uint64_t>, FusedTable> g_table_cache;
+std::map<std::pair<uint64_t, uint64_t>, XTable> g_xtable_cache;
+std::map<std::pair<uint64_t, uint64_t>, AutoTable> g_atable_cache;
+std::map<std::pair<std::pair<uint64_t, uint64_t>, int>, LzTable> g_ltable_cache;
+}  // namespace
+
 struct dnaf_ctx {
     int dev = 0;
     cudaStream_t stream = nullptr;
@@ -147,7 +159,7 @@ struct dnaf_ctx {
     uint64_t pass_text = 0;
     uint32_t fused_threads = 256;
     int cur_ob = 0;
-    std::map<std::pair<uint64_t, uint64_t>, FusedTable> table_cache;
+    std::map<std::pair<uint64_t, uint64_t>, FusedTable>& table_cache = g_table_cache;
     bool etab_ok = false;
     std::vector<double> bucket_p;          // minor-allele probability per bucket
     std::unordered_map<uint32_t, int> bucket_of;
@@ -155,6 +167,7 @@ struct dnaf_ctx {
     std::vector<uint64_t> ph;              // prefix byte model
     uint64_t ph_hash = 0;
     uint64_t samples_epoch = 0, seg_epoch = ~0ull;
+    uint64_t samples_hash = 0;             // FNV-1a of (n, sex vector): keys the sample-dependent tables in the process-wide caches
     std::vector<uint64_t> tables_sig;      // what d_ftables currently holds
     std::vector<uint8_t> h_sex;
     DevBuf d_crc4, d_xspan, d_tdesc, d_xspans, d_xdesc;
@@ -164,12 +177,12 @@ struct dnaf_ctx {
     DevBuf d_bucket, d_ovr_first, d_seginfo;   // implicit block descriptors of all-autosome passes (k_auto.cuh)
     std::vector<uint32_t> h_other;          // [S+1]: rows before r that do NOT take k_auto
     bool implicit_pass = false;
-    std::map<std::pair<uint64_t, uint64_t>, XTable> xtable_cache;
+    std::map<std::pair<uint64_t, uint64_t>, XTable>& xtable_cache = g_xtable_cache;
     std::vector<uint32_t> h_mspan, h_mpre_x;
-    std::map<std::pair<uint64_t, uint64_t>, AutoTable> atable_cache;
+    std::map<std::pair<uint64_t, uint64_t>, AutoTable>& atable_cache = g_atable_cache;
     // k_lz (k_lz.cuh): code tables per (bucket, starts-row) of the LZ tier in use (-z 4..9)
     DevBuf d_ltables;
-    std::map<std::pair<std::pair<uint64_t, uint64_t>, int>, LzTable> ltable_cache;
+    std::map<std::pair<std::pair<uint64_t, uint64_t>, int>, LzTable>& ltable_cache = g_ltable_cache;
     std::vector<uint64_t> ltables_sig;     // what d_ltables currently holds
     bool lz_ok = false;
     bool lz_attr_done = false;

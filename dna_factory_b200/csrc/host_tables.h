@@ -119,6 +119,7 @@ int ensure_tables(dnaf_ctx* c) {
         for (int v = 0; v < kVariants; ++v) sig.push_back(need[b * kVariants + v] ? pbits : 0);
     }
     if (sig != c->tables_sig) {
+        std::lock_guard<std::mutex> tables_lock(g_tables_mu);
         std::vector<FusedTable> tabs((size_t)nb * kVariants);
         memset(tabs.data(), 0, tabs.size() * sizeof(FusedTable));
         std::vector<AutoTable> atabs((size_t)nb * 2);
@@ -153,12 +154,12 @@ int ensure_tables(dnaf_ctx* c) {
                         cached = c->atable_cache.count(key) != 0;
                         family = 0;
                     } else if (v >= 10) {
-                        key = {pbits, base + (uint64_t)per_block + c->samples_epoch * 0x9E3779B97F4A7C15ull};
+                        key = {pbits, base + (uint64_t)per_block + c->samples_hash * 0x9E3779B97F4A7C15ull};
                         cached = c->xtable_cache.count(key) != 0;
                         family = 1;
                     } else {
                         const int cls = (v - 2) / 2;
-                        key = {pbits, base + (uint64_t)(cls + 1) * 1000003ull + c->samples_epoch * 0x9E3779B97F4A7C15ull};
+                        key = {pbits, base + (uint64_t)(cls + 1) * 1000003ull + c->samples_hash * 0x9E3779B97F4A7C15ull};
                         cached = c->table_cache.count(key) != 0;
                         family = 2 + cls;
                     }
@@ -218,7 +219,7 @@ int ensure_tables(dnaf_ctx* c) {
                 }
                 if (v >= 10) {   // X rows: k_x's tables
                     auto key = std::make_pair(pbits, (with_prefix ? c->ph_hash : 0x5bd1e995ull) * 31 + (uint64_t)per_block +
-                                                         c->samples_epoch * 0x9E3779B97F4A7C15ull);
+                                                         c->samples_hash * 0x9E3779B97F4A7C15ull);
                     auto it = c->xtable_cache.find(key);
                     if (it == c->xtable_cache.end()) {
                         XTable t = hosttab::make_x_table(p, c->h_xspans, per_block, with_prefix ? c->ph.data() : nullptr);
@@ -230,7 +231,7 @@ int ensure_tables(dnaf_ctx* c) {
                 }
                 const int cls = v < 2 ? -1 : (v >= 10 ? 100 : (v - 2) / 2);   // -1: autosome cells, 100: X cells
                 const uint64_t vkey = (with_prefix ? c->ph_hash : 0x5bd1e995ull) * 31 + (uint64_t)(cls + 1) * 1000003ull +
-                                      (cls >= 0 ? c->samples_epoch * 0x9E3779B97F4A7C15ull : 0);
+                                      (cls >= 0 ? c->samples_hash * 0x9E3779B97F4A7C15ull : 0);
                 auto key = std::make_pair(pbits, vkey);
                 auto it = c->table_cache.find(key);
                 if (it == c->table_cache.end()) {
@@ -335,6 +336,7 @@ int ensure_lz_tables(dnaf_ctx* c, int level) {
         c->lz_ok = true;
         return DNAF_OK;
     }
+    std::lock_guard<std::mutex> tables_lock(g_tables_mu);
     struct Job { int b, v; std::pair<std::pair<uint64_t, uint64_t>, int> key; };
     std::vector<Job> jobs;
     std::map<std::pair<std::pair<uint64_t, uint64_t>, int>, int> seen;
