@@ -1,7 +1,7 @@
 #!/bin/bash
-# per-kernel device times of bench steps (ncu, serialised launches): usage scripts/kernel_times.sh <out.csv> [rows-per-step]
-R=${2:-8192}
-CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --rows-per-step $R"
+# per-kernel device times of bench steps (ncu, serialised launches): usage scripts/kernel_times.sh <out.csv> [rows-per-step] [level]
+R=${2:-32768}; Z=${3:-2}
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras --rows-per-step $R --level $Z"
 $CMD > gpurun_out/plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum,smsp__thread_inst_executed_per_inst_executed.ratio,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active \
     --clock-control none -k regex:k_ -s 24 -c 24 --csv --log-file "$1" $CMD > gpurun_out/ncu1.log 2>&1
