@@ -404,8 +404,8 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     traffic, traffic_note = None, None
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-            tr = json.load(f)
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
+            tr = json.load(f)["k_auto" if args.level <= 2 else "k_lz"]
         traffic = tr["dram_bytes_per_launch"]
         traffic_note = "%s, one ncu --set full capture: %d-block launch emitting %.0f MB of text" % (
             tr["kernel"], tr["blocks"], tr["text_bytes_of_that_launch"] / 1e6)
@@ -417,7 +417,7 @@ def main():
     auto_text = sum(s["auto_text_bytes"] for s in stats)
     auto_launches = sum(s["auto_launches"] for s in stats)
     if ms_auto > 0:
-        achieved, kernel = auto_text / (ms_auto * 1e-3) / 1e9, ("k_auto" if args.level <= 3 else "k_lz")
+        achieved, kernel = auto_text / (ms_auto * 1e-3) / 1e9, ("k_auto" if args.level <= 2 else "k_lz")
     else:
         achieved, kernel = stage_achieved, dom.replace("ms_", "")
     roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
