@@ -225,6 +225,12 @@ def run_extras(eng, torch, stream, R, n_steps_total, arrays, orow, osamp, row_ba
         out["cli_to_file"] = cli_to_file(65536)
     except Exception as e:   # noqa: a full disk or a missing tmp dir must not cost the bench line
         out["cli_to_file"] = {"error": "%s: %s" % (type(e).__name__, e)}
+    # ---- BASELINE config 1 in full through the same CLI (200 samples x 100 000 SNPs: rows of 800 bytes take the
+    # generic three-kernel path), to set beside cpu_baseline_c1_full
+    try:
+        out["c1_full_cli"] = cli_to_file(100000, cases=100, controls=100)
+    except Exception as e:   # noqa
+        out["c1_full_cli"] = {"error": "%s: %s" % (type(e).__name__, e)}
     _lap("cli_to_file")
     # ---- allele-frequency chi-square of the draws (north_star), >= 1e8 calls
     out["allele_chi_square"] = allele_stats.chi_square_report(level=LEVEL, device=local_rank)
@@ -232,8 +238,8 @@ def run_extras(eng, torch, stream, R, n_steps_total, arrays, orow, osamp, row_ba
     return out
 
 
-def cli_to_file(snps, level=LEVEL):
-    """`pop_factory -s 10000 -c 10000 -x <snps> -f 0.01 -z 2 --gpu_select` of the re-hosted CLI into a temp dir."""
+def cli_to_file(snps, level=LEVEL, cases=N_CASES, controls=N_CONTROLS):
+    """`pop_factory -s <cases> -c <controls> -x <snps> -f 0.01 -z 2 --gpu_select` of the re-hosted CLI into a temp dir."""
     import contextlib
     import io
     import shutil
@@ -244,16 +250,16 @@ def cli_to_file(snps, level=LEVEL):
         buf = io.StringIO()
         t0 = time.perf_counter()
         with contextlib.redirect_stdout(buf):
-            pop_factory.main(["-s", str(N_CASES), "-c", str(N_CONTROLS), "-x", str(snps), "-f", str(MIN_MAF), "-z", str(level), "-p",
+            pop_factory.main(["-s", str(cases), "-c", str(controls), "-x", str(snps), "-f", str(MIN_MAF), "-z", str(level), "-p",
                               os.path.join(ROOT, "tests", "golden", "cli_small", "deleterious_config.yml"), "--outdir", d, "--seed", "123456", "--gpu_select"])
         wall = time.perf_counter() - t0
         import re
         m = re.findall(r"Finished write_vcf_snps chunk Elapsed time: ([0-9.]+) seconds", buf.getvalue())
         write_s = sum(float(x) for x in m)
-        calls = (N_CASES + N_CONTROLS) * snps
+        calls = (cases + controls) * snps
         size = os.path.getsize(os.path.join(d, "population.vcf.gz"))
         return {"calls_per_s_write_vcf_snps": calls / write_s if write_s else None, "calls_per_s_wall": calls / wall, "wall_s": wall,
-                "write_vcf_snps_s": write_s, "vcf_gz_bytes": size, "snps": snps, "samples": N_CASES + N_CONTROLS, "level": level}
+                "write_vcf_snps_s": write_s, "vcf_gz_bytes": size, "snps": snps, "samples": cases + controls, "level": level}
     finally:
         shutil.rmtree(d, ignore_errors=True)
 
