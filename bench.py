@@ -447,7 +447,7 @@ def main():
     # pipelined (kernels of pass i+1 run while pass i crosses PCIe), and while one context's last pass drains the
     # other uploads its step's SNP metadata and starts its kernels.  Every step still does its own H2D, kernels and
     # D2H inside the timed region.  (1 context: 5.3 ms per step, 2: 4.2-4.7 ms, PCIe floor 4.1 ms.)
-    n_ctx = 2
+    n_ctx = int(os.environ.get("DNAF_BENCH_CTX", "2"))
     engines = [eng] + [_native.Engine(local_rank) for _ in range(n_ctx - 1)]
     for e in engines[1:]:
         e.set_samples(sex, ctl)
