@@ -329,3 +329,22 @@ def test_reference_copy_is_byte_identical_and_runs():
         assert hashlib.sha256(open(os.path.join(make_ref.DEST, rel), "rb").read()).hexdigest() == digest
     r = ref_cli.run(20, 20, 300, 2, procs=2)
     assert r["calls"] == 12000 and r["write_s"] > 0 and r["vcf_bytes"] > 1000
+
+
+def test_bench_population_windows_do_not_depend_on_what_follows():
+    """bench.py's multi-GPU parity check regenerates a rank's FIRST window alone: the window's SNP rows and forced
+    cells must be the same whether 1 or 3 windows are drawn for that rank."""
+    import bench
+    one = bench.synth_population(64, rank=3, window=64)
+    three = bench.synth_population(192, rank=3, window=64)
+    assert np.array_equal(one[0], three[0]) and np.array_equal(one[1], three[1])
+    a, b = one[2].device_arrays(), three[2].device_arrays()
+    from dna_factory_b200 import host
+    b0 = host.slice_snps(b, 0, 64)
+    for k in ("chrom_class", "n_alleles", "thresholds", "prefix_off"):
+        assert np.array_equal(a[k], b0[k]), k
+    n = int(a["prefix_off"][-1])
+    assert bytes(a["prefix_bytes"][:n]) == bytes(b0["prefix_bytes"][:n])
+    r1, s1 = host.slice_overrides(one[3], one[4], 0, 64)
+    r3, s3 = host.slice_overrides(three[3], three[4], 0, 64)
+    assert np.array_equal(r1, r3) and np.array_equal(s1, s3) and len(r1) >= 2
