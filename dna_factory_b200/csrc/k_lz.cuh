@@ -39,7 +39,7 @@ constexpr uint32_t kLzNone = 0xFFFFu;      // prev[] entry / head value of "no e
 constexpr uint32_t kLzRegion = 4096;   // alleles per region (one warp's 32 spans)
 constexpr uint32_t kLzMaxKey = 9;      // alleles in a key (head tables have 2^(key+1) 32-bit entries per region)
 constexpr uint32_t kLzMaxDist = 16384; // alleles = 32768 bytes
-constexpr uint32_t kLzGood = 8;        // alleles: with a near match this long (or behind a match) the chain is searched a quarter as deep
+constexpr uint32_t kLzGood = 8;        // alleles: with a near match this long in hand the key chain is not walked
 
 struct LzCfg {
     uint32_t chain;   // far candidates examined per lookup
@@ -144,7 +144,7 @@ __host__ __device__ __forceinline__ uint32_t lz_extend(const Mem& mem, uint32_t 
 // Best match at allele s (k alleles at distance `da` alleles; k = 0: none), and s's own 32-allele window.
 // Set-up and the two near distances (4 and 8 bytes: j = s-2, s-4) are compared from the same three words that hold
 // s's own window, then the key chain of s is walked nearest first (own region, then the regions before it through
-// their heads), at most `depth` entries (a quarter of it once a match of kLzGood alleles is in hand).
+// their heads), at most `depth` entries -- unless a near match of kLzGood alleles is already in hand.
 template <class Mem>
 __host__ __device__ __forceinline__ void lz_lookup(const Mem& mem, uint32_t s, uint32_t aend, uint32_t nall, const LzCfg cfg,
                                                   uint32_t depth, uint32_t& best_k, uint32_t& best_da, uint32_t& ws0) {
@@ -170,8 +170,9 @@ __host__ __device__ __forceinline__ void lz_lookup(const Mem& mem, uint32_t s, u
     best_k = k2 > k1 ? k2 : k1;
     best_da = k2 > k1 ? 4u : 2u;
     if (best_k == 32u && limit > 32u) best_k = lz_extend(mem, s, s - best_da, limit);   // the nearer one goes on
-    if (depth && best_k < limit && best_k < cfg.nice && s + cfg.key <= nall) {
-        if (best_k >= kLzGood) depth = (depth + 3u) >> 2;
+    // not with a near match of kLzGood alleles in hand (zlib's good_length idea taken to its end: on the host twin,
+    // walking a quarter of the chain there or none of it gives the same ratio)
+    if (depth && best_k < limit && best_k < kLzGood && s + cfg.key <= nall) {
         const uint32_t key = (ws0 & ((1u << cfg.key) - 1u)) | ((s & 1u) << cfg.key);
         uint32_t reg = s / kLzRegion;
         uint32_t j = mem.prev(s);
@@ -200,7 +201,10 @@ __host__ __device__ __forceinline__ void lz_lookup(const Mem& mem, uint32_t s, u
 // chains together.  (Earlier shapes, measured: nested per-token loops left 18 of 32 threads active; a fully flat
 // one-candidate-per-trip state machine 13 of 32 -- every trip ran the code of every state some lane was in; one lookup
 // per trip with the lazy second lookup as a trip of its own 16 of 32 at -z 6 -- full-depth and quarter-depth lanes
-// mixed.)  nice: a match of that many alleles ends the search (zlib's nice_length).
+// mixed.  A two-phase variant -- near-match tokens emitted in a tight loop until the thread stands at an allele that
+// needs its chain, then all lanes walk together -- was 7 % faster at -z 3 and 3 % slower at -z 6: the rows that cost
+// the time are the common-minor-allele ones, where every token needs its chain.)
+// nice: a match of that many alleles ends the search (zlib's nice_length).
 template <class Mem, class Sink>
 __host__ __device__ __forceinline__ void lz_span_tokens(const Mem& mem, uint32_t a0, int nc, bool first_in_block, bool starts_row,
                                                         bool ends_row, bool ends_block, uint32_t nall, const LzCfg cfg, Sink& sink) {
