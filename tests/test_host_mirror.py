@@ -348,3 +348,23 @@ def test_bench_population_windows_do_not_depend_on_what_follows():
     r1, s1 = host.slice_overrides(one[3], one[4], 0, 64)
     r3, s3 = host.slice_overrides(three[3], three[4], 0, 64)
     assert np.array_equal(r1, r3) and np.array_equal(s1, s3) and len(r1) >= 2
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/dnaf_b200.h must be consumable by the reference's side of an FFI without a C++ compiler: a C99 program
+    includes it, links the library and calls the GPU-free entry points (tests/c/abi_smoke.c)."""
+    import shutil
+    import subprocess
+    from dna_factory_b200 import _native
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    _native.load()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "abi_smoke"
+    lib_dir = os.path.dirname(_native.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(root, "include"),
+                           os.path.join(root, "tests", "c", "abi_smoke.c"), "-o", str(exe), "-L", lib_dir, "-ldnaf_b200",
+                           "-Wl,-rpath," + lib_dir])
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert r.stdout.startswith("abi 5 ok")
