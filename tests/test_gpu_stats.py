@@ -13,12 +13,10 @@ The text comes out of the fused kernels (k_auto / k_lz) through the C ABI and is
 import numpy as np
 import pytest
 
-pytestmark = pytest.mark.gpu
+from dna_factory_b200.allele_stats import chi_square_report
 
 
-from dna_factory_b200.allele_stats import chi_square_report  # noqa: E402
-
-
+@pytest.mark.gpu
 @pytest.mark.parametrize("level", [2, 6])
 def test_allele_frequencies_chi_square(level):
     r = chi_square_report(level=level)
