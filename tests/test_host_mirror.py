@@ -368,3 +368,20 @@ def test_header_is_plain_c_and_links(tmp_path):
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
     assert r.stdout.startswith("abi 5 ok")
+
+
+def test_bench_reference_arm_runs_the_unmodified_reference():
+    """bench.py --impl reference / cpu_baseline: the reference CLI from oracle/_ref, timed by its own write_vcf_snps
+    timer (pop_factory.py:417), at a toy size here."""
+    import bench
+    from oracle import make_ref
+    make_ref.materialise()
+    if not make_ref.available():
+        pytest.skip("oracle/_ref not materialised (no reference tree here)")
+    saved = bench.N_CASES, bench.N_CONTROLS
+    bench.N_CASES = bench.N_CONTROLS = 50
+    try:
+        r = bench.python_reference_run(1, 0, rows=200)
+    finally:
+        bench.N_CASES, bench.N_CONTROLS = saved
+    assert r["value"] > 0 and r["procs"] >= 1 and "unmodified reference CLI" in r["sample"]
