@@ -1,10 +1,14 @@
-"""Ad-hoc: ratio and device-only rate of every -z level on the C2 shape (20 000 samples), one 32768-row window."""
+"""Ad-hoc: ratio and device-only rate of every -z level on the C2 shape (20 000 samples), one 32768-row window;
+   python scripts/level_probe.py [rows] [samples]."""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import bench
 from dna_factory_b200 import _native
 R = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
+if len(sys.argv) > 2:                      # another sample count, e.g. 100000 for the C4 shape
+    bench.N_CASES = int(sys.argv[2]) // 2
+    bench.N_CONTROLS = int(sys.argv[2]) - bench.N_CASES
 sex, ctl, table, orow, osamp = bench.synth_population(R, 0, window=R)
 eng = _native.Engine(0)
 eng.set_samples(sex, ctl); eng.set_snps(**table.device_arrays()); eng.set_overrides(orow, osamp)
