@@ -421,7 +421,10 @@ __device__ __forceinline__ uint32_t auto_span_crc(const AutoArgs& a, const Fused
     return crc;
 }
 
-__global__ void __maxnreg__(56) k_auto(const AutoArgs a) {
+#ifndef DNAF_AUTO_REGS
+#define DNAF_AUTO_REGS 56   // 7 blocks of 160 threads per SM; 64 (6 blocks) and 48 (spills) measured slower
+#endif
+__global__ void __maxnreg__(DNAF_AUTO_REGS) k_auto(const AutoArgs a) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const uint32_t tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31u, wid = tid >> 5;
     uint2* s_lut = reinterpret_cast<uint2*>(smem_raw);
